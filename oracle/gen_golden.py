@@ -1,0 +1,182 @@
+"""Generate tests/golden/*.npz by running the REAL reference (container only; needs /root/reference).
+
+    python -m oracle.gen_golden            # writes tests/golden/
+    python -m oracle.gen_golden --check    # additionally runs the oracle port and prints max deviations
+
+The reference model (``compress.models.ChannelProgresssiveWACNN``, imported unmodified from
+/root/reference/src with the native coder compiled into oracle/_ref) is filled with
+``progressivecodec_b200.synthetic.apply_synthetic_weights`` (name-keyed, so every implementation
+gets the same weights) and run on seeded inputs.  Saved per case: bit streams, reconstructions,
+likelihood tensors and intermediate latents.  Fixtures are small (64x128 inputs) so they can live
+in git; full-size parity is checked on the GPU box against the oracle port, which these fixtures pin.
+"""
+from __future__ import annotations
+
+import argparse
+import io
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (ctor kwargs, input shape)
+    "authors": (dict(multiple_decoder=True, multiple_encoder=False, multiple_hyperprior=True, delta_encode=True,
+                     support_progressive_slices=5, mask_policy="point-based-std"), (1, 3, 64, 128)),
+    "multienc": (dict(multiple_decoder=True, multiple_encoder=True, multiple_hyperprior=True, delta_encode=True,
+                      support_progressive_slices=5, mask_policy="point-based-std"), (2, 3, 64, 64)),
+    "allscalable": (dict(multiple_decoder=True, multiple_encoder=False, multiple_hyperprior=True, delta_encode=True,
+                         support_progressive_slices=5, mask_policy="point-based-std", all_scalable=True),
+                    (1, 3, 64, 64)),
+    "plain": (dict(multiple_decoder=True, multiple_encoder=True, multiple_hyperprior=False, delta_encode=False,
+                   support_progressive_slices=0, mask_policy="two-levels"), (1, 3, 64, 64)),
+}
+QUALITIES = [0, 0.05, 0.5, 1.25, 5, 10]
+FWD_QUALITIES = [0, 0.5, 5, 10]
+
+
+def synthetic_image(shape, seed: int) -> torch.Tensor:
+    """Seeded low-pass-filtered noise in [0,1] (SURVEY.md §8d 'Synthetic inputs')."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = torch.rand(*shape, generator=g)
+    x = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(x, (2, 2, 2, 2), mode="reflect"), 5, 1)
+    return x.contiguous()
+
+
+def pack_strings(strings) -> dict:
+    """strings = [list_over_slices[list_over_batch[bytes]], list_over_batch[bytes]] -> flat uint8 + lengths."""
+    ys, zs = strings
+    flat = [s for sl in ys for s in sl] + list(zs)
+    lens = np.array([len(s) for s in flat], dtype=np.int64)
+    blob = np.frombuffer(b"".join(flat), dtype=np.uint8) if lens.sum() else np.zeros(0, np.uint8)
+    return {"blob": blob, "lens": lens, "n_slices": np.int64(len(ys)), "batch": np.int64(len(zs))}
+
+
+def unpack_strings(d, prefix: str):
+    blob, lens = d[prefix + "blob"], d[prefix + "lens"]
+    ns, b = int(d[prefix + "n_slices"]), int(d[prefix + "batch"])
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    flat = [blob[offs[i]:offs[i + 1]].tobytes() for i in range(len(lens))]
+    ys = [flat[s * b:(s + 1) * b] for s in range(ns)]
+    zs = flat[ns * b:]
+    return [ys, zs]
+
+
+def build_reference(kwargs):
+    from . import build_ref
+
+    build_ref.import_reference()
+    warnings.filterwarnings("ignore")
+    from compress.models import ChannelProgresssiveWACNN  # type: ignore
+
+    sys.path.insert(0, ROOT)
+    from progressivecodec_b200.synthetic import apply_synthetic_weights
+
+    out = io.StringIO()
+    stdout, sys.stdout = sys.stdout, out  # the reference constructor print()s
+    try:
+        torch.manual_seed(0)
+        net = ChannelProgresssiveWACNN(lmbda_list=[0.005, 0.05], **kwargs)
+    finally:
+        sys.stdout = stdout
+    net.eval()
+    apply_synthetic_weights(net, seed=0)
+    net.update(force=True)
+    return net
+
+
+def run_case(name: str, check: bool):
+    kwargs, shape = CASES[name]
+    net = build_reference(kwargs)
+    x = synthetic_image(shape, seed=len(name))
+    rec = {"x": x.numpy()}
+    pol = kwargs["mask_policy"]
+    with torch.no_grad():
+        for q in QUALITIES:
+            if pol == "two-levels" and q not in (0, 10):
+                continue
+            c = net.compress(x, quality=q, mask_pol=pol)
+            d = net.decompress(c["strings"], c["shape"], quality=q, mask_pol=pol)
+            tag = f"q{q}_"
+            for k, v in pack_strings(c["strings"]).items():
+                rec[tag + k] = v
+            rec[tag + "shape"] = np.array(list(c["shape"]), dtype=np.int64)
+            rec[tag + "x_hat"] = d["x_hat"].numpy()
+            if c["masks"]:
+                rec[tag + "mask_sum"] = np.array([float(m.sum()) for m in c["masks"]])
+        for q in FWD_QUALITIES:
+            if pol == "two-levels" and q not in (0, 10):
+                continue
+            o = net.forward_single_quality(x, q, mask_pol=pol, training=False)
+            tag = f"fsq{q}_"
+            rec[tag + "x_hat"] = o["x_hat"].numpy()
+            rec[tag + "lik_y"] = o["likelihoods"]["y"].numpy()
+            rec[tag + "lik_z"] = o["likelihoods"]["z"].numpy()
+            rec[tag + "y_hat"] = o["y_hat"].numpy()
+        ql = [0, 0.5, 5, 10] if pol != "two-levels" else [0, 10]
+        o = net.forward(x, quality=ql, mask_pol=pol, training=False)
+        rec["fwd_qualities"] = np.array(ql, dtype=np.float64)
+        rec["fwd_x_hat"] = o["x_hat"].numpy()
+        rec["fwd_lik_y"] = o["likelihoods"]["y"].numpy()
+        rec["fwd_lik_y_prog"] = o["likelihoods"]["y_prog"].numpy()
+        rec["fwd_lik_z"] = o["likelihoods"]["z"].numpy()
+    # entropy tables (update() output) — pins GaussianTables.build / BottleneckTables.rebuild
+    gc, eb = net.gaussian_conditional, net.entropy_bottleneck
+    rec["gc_cdf"] = gc._quantized_cdf.numpy().astype(np.int32)
+    rec["gc_cdf_length"] = gc._cdf_length.numpy().astype(np.int32)
+    rec["gc_offset"] = gc._offset.numpy().astype(np.int32)
+    rec["gc_scale_table"] = gc.scale_table.numpy()
+    rec["eb_cdf"] = eb._quantized_cdf.numpy().astype(np.int32)
+    rec["eb_cdf_length"] = eb._cdf_length.numpy().astype(np.int32)
+    rec["eb_offset"] = eb._offset.numpy().astype(np.int32)
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, f"{name}.npz")
+    np.savez_compressed(path, **rec)
+    print(f"[golden] {name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(rec)} arrays")
+    if check:
+        from .codec_port import CodecConfig, OracleCodec
+
+        orc = OracleCodec(net.state_dict(), CodecConfig(**kwargs))
+        for q in QUALITIES:
+            if pol == "two-levels" and q not in (0, 10):
+                continue
+            c = orc.compress(x, quality=q, mask_pol=pol)
+            ref = unpack_strings(rec, f"q{q}_")
+            same = c["strings"][0] == ref[0] and c["strings"][1] == ref[1]
+            d = orc.decompress(ref, tuple(rec[f"q{q}_shape"]), quality=q, mask_pol=pol)
+            err = float(np.abs(d["x_hat"].numpy() - rec[f"q{q}_x_hat"]).max())
+            print(f"   q={q}: strings identical={same}, x_hat max|d|={err:.3g}")
+        for q in FWD_QUALITIES:
+            if pol == "two-levels" and q not in (0, 10):
+                continue
+            o = orc.forward_single_quality(x, q, mask_pol=pol)
+            e1 = float(np.abs(o["x_hat"].numpy() - rec[f"fsq{q}_x_hat"]).max())
+            e2 = float(np.abs(o["likelihoods"]["y"].numpy() - rec[f"fsq{q}_lik_y"]).max())
+            e3 = float(np.abs(o["likelihoods"]["z"].numpy() - rec[f"fsq{q}_lik_z"]).max())
+            print(f"   fsq q={q}: x_hat {e1:.3g} lik_y {e2:.3g} lik_z {e3:.3g}")
+        o = orc.forward(x, quality=list(rec["fwd_qualities"]), mask_pol=pol)
+        print("   forward: x_hat %.3g lik_y %.3g lik_y_prog %.3g lik_z %.3g" % (
+            float(np.abs(o["x_hat"].numpy() - rec["fwd_x_hat"]).max()),
+            float(np.abs(o["likelihoods"]["y"].numpy() - rec["fwd_lik_y"]).max()),
+            float(np.abs(o["likelihoods"]["y_prog"].numpy() - rec["fwd_lik_y_prog"]).max()),
+            float(np.abs(o["likelihoods"]["z"].numpy() - rec["fwd_lik_z"]).max())))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--cases", nargs="*", default=list(CASES))
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count() or 1)
+    for name in a.cases:
+        run_case(name, a.check)
+
+
+if __name__ == "__main__":
+    main()
