@@ -1,0 +1,223 @@
+/*
+ * pcodec_b200 — C-ABI of the B200 (sm_100a) hot path of the progressive codec.
+ *
+ * Drop-in boundary for EIDOSLAB/ProgressiveCodec's inference path
+ * (ChannelProgresssiveWACNN.forward / compress / decompress).  Every entry point takes plain
+ * pointers + sizes + an explicit CUDA stream (passed as void*, i.e. a cudaStream_t) and returns an
+ * int status: 0 = OK, >0 = a pcodec error (PCODEC_ERR_*), <0 = -(cudaError_t).
+ * No torch types cross this boundary.  Unless stated otherwise every pointer is a DEVICE pointer.
+ *
+ * Reference interfaces replaced (paths under /root/reference/src/compress/):
+ *   cpp_exts/rans/rans_interface.cpp:99-204   RansEncoder / BufferedRansEncoder   -> pcodec_rans_encode_batch
+ *   cpp_exts/rans/rans_interface.cpp:206-350  RansDecoder                         -> pcodec_rans_decode_batch
+ *   cpp_exts/ops/ops.cpp:10-67                pmf_to_quantized_cdf                -> pcodec_pmf_to_quantized_cdf
+ *   layers/masking.py:205-223                 ChannelMask 'point-based-std'       -> pcodec_quantile_threshold
+ *   entropy_models/entropy_models.py:126-165, 661-666 quantize/dequantize/build_indexes
+ *                                                                                 -> pcodec_slice_quantize / _indexes / _dequantize
+ *   entropy_models/entropy_models.py:626-659  GaussianConditional likelihood      -> pcodec_slice_quantize (lik output)
+ *   entropy_models/entropy_models.py:400-433, 446-522 EntropyBottleneck           -> pcodec_bottleneck_*
+ *   models/utils.py:186-204, layers/layers.py:15-29, layers/gdn.py:50-63          -> pcodec_conv_taps
+ *   layers/win_attention.py:84-115,153-207    shifted-window attention core       -> pcodec_window_attention
+ *
+ * Activation layout: NHWC fp32 ("pixel-major"): element (n,h,w,c) of a tensor with pixel stride PS
+ * lives at base[((n*H + h)*W + w)*PS + c]; PS >= C lets several tensors share one concat buffer.
+ * Symbol / index / likelihood / mask tensors that feed the entropy coder use the reference's
+ * NCHW order, because that order defines the bit stream (entropy_models.py:227-235).
+ */
+#ifndef PCODEC_B200_H_
+#define PCODEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCODEC_OK 0
+#define PCODEC_ERR_BAD_ARG 1
+#define PCODEC_ERR_UNSUPPORTED 2
+#define PCODEC_ERR_OVERFLOW 3 /* an output / scratch capacity was too small; retry with a larger one */
+
+/* library / device info ------------------------------------------------------------------- */
+int pcodec_version(void);
+/* HOST. Fills sm count and compute capability of the current device; returns status. */
+int pcodec_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* HOST. Number of kernels this library has launched since load / last reset (bench 'gpu_launches'). */
+int64_t pcodec_launch_count(void);
+void pcodec_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Entropy coder
+ * ---------------------------------------------------------------------------------------- */
+
+/* HOST pointers. ops.cpp:10-67. cdf_out has n+1 entries. Returns PCODEC_ERR_BAD_ARG when no frequency
+ * can be stolen for a zero-width bin (the reference asserts). */
+int pcodec_pmf_to_quantized_cdf(const float *pmf, int n, int precision, uint32_t *cdf_out);
+
+/* Batched rANS encode of n_streams independent streams of n_per_stream symbols each
+ * (one stream = one (image, slice) of the reference: rans_interface.cpp:193-204).
+ *   symbols, indexes : int32 [n_streams][n_per_stream]
+ *   cdfs             : int32 [n_tables][cdf_stride]; cdf_sizes, offsets: int32 [n_tables]
+ *   scratch          : uint32 [n_streams][scratch_words]  (per-stream backward write area)
+ *   stream_words     : int32 [n_streams] workspace; on return the number of 32-bit words of each stream
+ *   out_bytes        : the streams, concatenated in stream order; capacity out_cap bytes
+ *   out_offsets      : int64 [n_streams+1] byte offsets into out_bytes
+ *   status           : int32 [1], set to PCODEC_ERR_OVERFLOW by the device when scratch_words or out_cap
+ *                      was too small (the host reads it together with out_offsets)
+ * The bytes of every stream are identical to RansEncoder.encode_with_indexes on the same inputs. */
+int pcodec_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int n_streams, int64_t n_per_stream,
+                             const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
+                             int n_tables, uint32_t *scratch, int64_t scratch_words, int32_t *stream_words,
+                             uint8_t *out_bytes, int64_t out_cap, int64_t *out_offsets, int32_t *status, void *stream);
+
+/* Batched rANS decode (rans_interface.cpp:206-275).  in_bytes/in_offsets as produced by the encoder (every
+ * stream must start 4-byte aligned, i.e. offsets are multiples of 4, which holds for rANS word streams).
+ *   out_symbols : int32 [n_streams][n_per_stream] */
+int pcodec_rans_decode_batch(const uint8_t *in_bytes, const int64_t *in_offsets, int n_streams, int64_t n_per_stream,
+                             const int32_t *indexes, const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes,
+                             const int32_t *offsets, int n_tables, int32_t *out_symbols, void *stream);
+
+/* HOST-only scalar walk over the same state arithmetic as the kernels (csrc/rans_core.h); exists so CPU unit
+ * tests can pin that arithmetic against the oracle.  Not used by the product path.  Words are written at the END
+ * of `words`; returns the number of words used or -1 on overflow. */
+int64_t pcodec_selftest_rans_core_encode(const int32_t *symbols, const int32_t *indexes, int64_t n, const int32_t *cdfs,
+                                         int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
+                                         uint32_t *words, int64_t cap_words);
+
+/* ------------------------------------------------------------------------------------------
+ * Variance-aware masking + quantisation + CDF index
+ * ---------------------------------------------------------------------------------------- */
+
+/* torch.quantile(scale[b].ravel(), q) for every image b, bit-compatible with ATen's linear interpolation
+ * (masking.py:216).  scale: NHWC fp32 [B][HW][ps] of which C channels are used; thr: fp32 [B].
+ * workspace: uint32 [B][4] scratch. */
+int pcodec_quantile_threshold(const float *scale, int batch, int64_t hw, int channels, int pixel_stride, float q,
+                              float *thr, uint32_t *workspace, void *stream);
+
+/* mask modes */
+#define PCODEC_MASK_ONES 0      /* pr >= 10, base slices, 'two-levels' pr != 0 */
+#define PCODEC_MASK_ZEROS 1     /* pr == 0 */
+#define PCODEC_MASK_THRESHOLD 2 /* mask = scale >= thr[b] */
+
+/* Fused encoder-side slice step (CHProg_cnn.py:744-755, 819-834 / forward :626-632):
+ *   v      = y - (y_sub ? y_sub : 0) - mu          (delta_encode subtracts the base slice first)
+ *   m      = mask(scale)                            (mode above)
+ *   sym    = rint(v * m)  [compress]   or   rint(v) * m  [forward]; both are the same integers
+ *   index  = #{ j < n_levels-1 : table[j] < max(scale*m, scale_bound) }
+ *   y_hat  = sym + mu
+ *   lik    = Gaussian likelihood of sym under max(scale*m, bound), lower-bounded 1e-9 (optional)
+ * Inputs are NHWC with their own pixel strides; symbols/indexes/mask/lik are written in NCHW order
+ * [B][C][H*W]; y_hat is NHWC with its own stride.  Any of symbols/indexes/mask_out/lik/y_hat may be NULL. */
+int pcodec_slice_quantize(const float *y, int y_ps, const float *y_sub, int y_sub_ps, const float *mu, int mu_ps,
+                          const float *scale, int scale_ps, int batch, int64_t hw, int channels, int mask_mode,
+                          const float *thr, const float *scale_table, int n_levels, float scale_bound,
+                          int32_t *symbols, int32_t *indexes, float *mask_out, float *lik, float *y_hat, int y_hat_ps,
+                          void *stream);
+
+/* Decoder-side: index (and mask) only (CHProg_cnn.py:891, 960-968). */
+int pcodec_slice_indexes(const float *scale, int scale_ps, int batch, int64_t hw, int channels, int mask_mode,
+                         const float *thr, const float *scale_table, int n_levels, float scale_bound,
+                         int32_t *indexes, void *stream);
+
+/* Decoder-side: y_hat = sym + mu (CHProg_cnn.py:894-896); symbols NCHW int32, mu / y_hat NHWC. */
+int pcodec_slice_dequantize(const int32_t *symbols, const float *mu, int mu_ps, int batch, int64_t hw, int channels,
+                            float *y_hat, int y_hat_ps, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * EntropyBottleneck (z path)
+ * ---------------------------------------------------------------------------------------- */
+
+/* symbols = rint(z - median[c]) (NCHW int32), indexes = c, z_hat = sym + median[c] (NHWC).  z: NHWC. */
+int pcodec_bottleneck_quantize(const float *z, int z_ps, const float *medians, int batch, int64_t hw, int channels,
+                               int32_t *symbols, int32_t *indexes, float *z_hat, int z_hat_ps, void *stream);
+/* z_hat = sym + median[c] from decoded NCHW symbols; also (re)writes indexes when non-NULL. */
+int pcodec_bottleneck_dequantize(const int32_t *symbols, const float *medians, int batch, int64_t hw, int channels,
+                                 float *z_hat, int z_hat_ps, void *stream);
+/* indexes[b][c][hw] = c */
+int pcodec_bottleneck_indexes(int batch, int64_t hw, int channels, int32_t *indexes, void *stream);
+/* Factorised-density likelihood of z_hat (entropy_models.py:421-433), NCHW output.
+ * params: per channel 58 floats: softplus(matrix0..4) (3,9,9,9,3), bias0..4 (3,3,3,3,1), tanh(factor0..3) (3,3,3,3). */
+int pcodec_bottleneck_likelihood(const float *z_hat, int z_ps, const float *params, int batch, int64_t hw, int channels,
+                                 float *lik, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution as a sum of shifted-tap GEMMs (implicit GEMM, NHWC)
+ * ---------------------------------------------------------------------------------------- */
+
+#define PCODEC_MAX_SEGMENTS 4
+#define PCODEC_MAX_TAPS 25
+
+/* epilogues: acc is the fp32 accumulator + bias[co] */
+#define PCODEC_EPI_LINEAR 0        /* acc */
+#define PCODEC_EPI_GELU 1          /* gelu_erf(acc) */
+#define PCODEC_EPI_ADD 2           /* acc + r1 */
+#define PCODEC_EPI_ADD_GELU 3      /* gelu_erf(acc + r1)                     (ResidualUnit, layers.py:52-58) */
+#define PCODEC_EPI_GATE 4          /* r2 * sigmoid(acc) + r1                 (Win_noShift_Attention, layers.py:69-75) */
+#define PCODEC_EPI_GDN 5           /* r1 * rsqrt(acc)  with A = x*x          (gdn.py:53-63) */
+#define PCODEC_EPI_IGDN 6          /* r1 * sqrt(acc) */
+#define PCODEC_EPI_LRP 7           /* r1 + 0.5*tanh(acc) (+ r2 if given)     (CHProg_cnn.py:759-762, 840-843) */
+#define PCODEC_EPI_CLAMP01 8       /* min(max(acc,0),1)                      (CHProg_cnn.py:909, 988) */
+
+#define PCODEC_FLAG_SQUARE_INPUT 1   /* A = x*x (GDN) */
+#define PCODEC_FLAG_PIXEL_SHUFFLE2 2 /* output channel co -> pixel (2h + (co>>1&1), 2w + (co&1)), channel co>>2; applied
+                                        after the epilogue (subpel_conv3x3, layers.py:20-24) */
+
+typedef struct {
+  const float *ptr; /* NHWC base of this channel segment */
+  int channels;     /* channels taken from this segment (multiple of 4) */
+  int pixel_stride; /* floats between consecutive pixels */
+} pcodec_segment;
+
+typedef struct {
+  /* input: virtual channel-concatenation of n_segments tensors sharing [batch, in_h, in_w] */
+  pcodec_segment seg[PCODEC_MAX_SEGMENTS];
+  int n_segments;
+  int batch, in_h, in_w;
+  /* taps: out(h,w) += in(h*in_step + dy[t], w*in_step + dx[t]) . W[t]; zero outside the input */
+  int n_taps;
+  int8_t dy[PCODEC_MAX_TAPS], dx[PCODEC_MAX_TAPS];
+  int in_step;
+  /* weights: fp32 [n_taps][cin_total][cout] (cout contiguous); bias fp32 [cout] or NULL */
+  const float *weight;
+  const float *bias;
+  int cin_total, cout;
+  /* output grid: M = batch*grid_h*grid_w GEMM rows; row (n,h,w) is stored at pixel
+   * (h*out_step + out_off_y, w*out_step + out_off_x) of an [batch, out_h, out_w] NHWC tensor */
+  int grid_h, grid_w, out_step, out_off_y, out_off_x, out_h, out_w;
+  float *out;
+  int out_pixel_stride;
+  /* epilogue */
+  int epilogue, flags;
+  const float *r1; int r1_pixel_stride; /* indexed like `out` (same pixel, same channel) */
+  const float *r2; int r2_pixel_stride;
+} pcodec_conv_desc;
+
+/* HOST descriptor, DEVICE tensors.  impl: 0 = auto, 1 = fp32 SIMT, 2 = tcgen05 3xTF32 (error if the shape is unsupported). */
+int pcodec_conv_taps(const pcodec_conv_desc *desc, int impl, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Shifted-window attention core (win_attention.py:84-115, 153-207)
+ * ---------------------------------------------------------------------------------------- */
+/* qkv: NHWC [B][H][W][3*C] (q | k | v, each head-major), out: NHWC [B][H][W][C] = softmax(q k^T * scale + relpos
+ * + shift mask) v, already un-shifted back to image coordinates.  rel_bias: fp32 [heads][T][T] with T = ws*ws. */
+int pcodec_window_attention(const float *qkv, int qkv_ps, float *out, int out_ps, const float *rel_bias, int batch,
+                            int height, int width, int channels, int heads, int window, int shift, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout helpers
+ * ---------------------------------------------------------------------------------------- */
+/* NCHW [B][C][HW] -> NHWC (pixel stride dst_ps, channels beyond C up to c_pad are zero-filled). */
+int pcodec_nchw_to_nhwc(const float *src, float *dst, int batch, int channels, int64_t hw, int dst_ps, int c_pad,
+                        void *stream);
+/* Patch extraction for the first analysis conv (3 input channels are too few for a 16-channel K chunk):
+ * src NCHW [B][C][H][W] -> dst NHWC [B][OH][OW][k_pad] with dst[.., (ky*k+kx)*C + c] = src[n][c][oh*stride+ky-pad][ow*stride+kx-pad]
+ * (zero outside the image and for entries >= k*k*C). */
+int pcodec_im2col_nchw(const float *src, float *dst, int batch, int channels, int height, int width, int k, int stride,
+                       int pad, int out_h, int out_w, int k_pad, void *stream);
+/* NHWC (first C channels, pixel stride src_ps) -> NCHW. */
+int pcodec_nhwc_to_nchw(const float *src, int src_ps, float *dst, int batch, int channels, int64_t hw, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCODEC_B200_H_ */

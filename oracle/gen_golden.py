@@ -136,6 +136,9 @@ def run_case(name: str, check: bool):
     rec["eb_cdf_length"] = eb._cdf_length.numpy().astype(np.int32)
     rec["eb_offset"] = eb._offset.numpy().astype(np.int32)
     os.makedirs(GOLD, exist_ok=True)
+    with open(os.path.join(GOLD, f"{name}_state_dict_keys.txt"), "w") as f:
+        for k, v in net.state_dict().items():
+            f.write(f"{k} {tuple(v.shape)} {v.dtype}\n")
     path = os.path.join(GOLD, f"{name}.npz")
     np.savez_compressed(path, **rec)
     print(f"[golden] {name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(rec)} arrays")

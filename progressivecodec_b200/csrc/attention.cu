@@ -1,0 +1,139 @@
+// Shifted-window multi-head self-attention core (reference: layers/win_attention.py:84-115, 153-207).
+//
+// The qkv and proj Linear layers are 1x1 convolutions on the NHWC tensor (pcodec_conv_taps); this kernel does
+// everything between them without materialising torch.roll / window_partition / window_reverse copies: a
+// (window, head) CTA gathers its T = ws*ws tokens straight from the rolled pixel positions, adds the
+// relative-position bias and the SW-MSA region mask (-100), soft-maxes and writes P.V back to the un-rolled
+// pixel.  T is 64 (ws 8) or 16 (ws 4); head_dim 24 / 40 / 80.
+#include "common.cuh"
+
+namespace {
+
+template <int T>
+__global__ void __launch_bounds__(T)
+window_attention_kernel(const float *__restrict__ qkv, int qkv_ps, float *__restrict__ out, int out_ps,
+                        const float *__restrict__ rel_bias, int H, int W, int C, int heads, int ws, int shift) {
+  extern __shared__ float smem[];
+  const int hd = C / heads;
+  const int ldk = hd + 1;
+  float *sq = smem;             // [T][ldk]
+  float *sk = sq + T * ldk;     // [T][ldk]
+  float *sv = sk + T * ldk;     // [T][hd]
+  __shared__ int s_region[T];
+
+  const int nww = W / ws, nwh = H / ws;
+  const int win = blockIdx.x % (nwh * nww);
+  const int b = blockIdx.x / (nwh * nww);
+  const int head = blockIdx.y;
+  const int wi = win / nww, wj = win % nww;
+  const int i = threadIdx.x;  // token index inside the window: (i / ws, i % ws)
+  const int hs = wi * ws + i / ws, wsft = wj * ws + i % ws;  // coordinates in the rolled image
+  const int ph = (hs + shift) % H, pw = (wsft + shift) % W;  // source / destination pixel
+  const int64_t pix = ((int64_t)b * H + ph) * W + pw;
+  const float scale = rsqrtf((float)hd);
+  {
+    const float *src = qkv + pix * qkv_ps + head * hd;
+    for (int dch = 0; dch < hd; ++dch) {
+      sq[i * ldk + dch] = __fmul_rn(src[dch], scale);
+      sk[i * ldk + dch] = src[C + dch];
+      sv[i * hd + dch] = src[2 * C + dch];
+    }
+    int region = 0;
+    if (shift > 0) {
+      const int rh = hs < H - ws ? 0 : (hs < H - shift ? 1 : 2);
+      const int rw = wsft < W - ws ? 0 : (wsft < W - shift ? 1 : 2);
+      region = rh * 3 + rw;
+    }
+    s_region[i] = region;
+  }
+  __syncthreads();
+
+  float s[T];
+  const float *bias = rel_bias + ((int64_t)head * T + i) * T;
+  const int my_region = s_region[i];
+#pragma unroll
+  for (int j = 0; j < T; ++j) s[j] = 0.f;
+  for (int dch = 0; dch < hd; ++dch) {
+    const float qv = sq[i * ldk + dch];
+#pragma unroll
+    for (int j = 0; j < T; ++j) s[j] = fmaf(qv, sk[j * ldk + dch], s[j]);
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    float v = s[j] + __ldg(bias + j);
+    if (shift > 0 && s_region[j] != my_region) v += -100.0f;
+    s[j] = v;
+    mx = fmaxf(mx, v);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    s[j] = expf(s[j] - mx);
+    sum += s[j];
+  }
+  const float inv = 1.0f / sum;
+  float *dst = out + pix * out_ps + head * hd;
+  for (int dch = 0; dch < hd; ++dch) {
+    float o = 0.f;
+#pragma unroll
+    for (int j = 0; j < T; ++j) o = fmaf(s[j] * inv, sv[j * hd + dch], o);
+    dst[dch] = o;
+  }
+}
+
+__global__ void im2col_nchw_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int H, int W, int k,
+                                   int stride, int pad, int OH, int OW, int k_pad, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int kk = (int)(e % k_pad);
+  int64_t t = e / k_pad;
+  const int ow = (int)(t % OW); t /= OW;
+  const int oh = (int)(t % OH);
+  const int64_t n = t / OH;
+  float v = 0.f;
+  if (kk < k * k * C) {
+    const int c = kk % C, tap = kk / C;
+    const int ky = tap / k, kx = tap % k;
+    const int iy = oh * stride + ky - pad, ix = ow * stride + kx - pad;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(src + ((n * C + c) * H + iy) * (int64_t)W + ix);
+  }
+  dst[e] = v;
+}
+
+}  // namespace
+
+extern "C" int pcodec_window_attention(const float *qkv, int qkv_ps, float *out, int out_ps, const float *rel_bias,
+                                       int batch, int height, int width, int channels, int heads, int window,
+                                       int shift, void *stream) {
+  if (!qkv || !out || !rel_bias || batch <= 0 || heads <= 0 || channels % heads != 0) return PCODEC_ERR_BAD_ARG;
+  if (window <= 0 || height % window != 0 || width % window != 0 || shift < 0 || shift >= window)
+    return PCODEC_ERR_BAD_ARG;
+  const int T = window * window, hd = channels / heads;
+  const size_t smem = sizeof(float) * ((size_t)2 * T * (hd + 1) + (size_t)T * hd);
+  dim3 grid((unsigned)(batch * (height / window) * (width / window)), (unsigned)heads);
+  cudaStream_t st = as_stream(stream);
+  if (T == 64) {
+    if (smem > 48 * 1024)
+      PCODEC_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem));
+    window_attention_kernel<64><<<grid, 64, smem, st>>>(qkv, qkv_ps, out, out_ps, rel_bias, height, width, channels,
+                                                        heads, window, shift);
+  } else if (T == 16) {
+    window_attention_kernel<16><<<grid, 16, smem, st>>>(qkv, qkv_ps, out, out_ps, rel_bias, height, width, channels,
+                                                        heads, window, shift);
+  } else {
+    return PCODEC_ERR_UNSUPPORTED;
+  }
+  PCODEC_RETURN_LAUNCH();
+}
+
+extern "C" int pcodec_im2col_nchw(const float *src, float *dst, int batch, int channels, int height, int width, int k,
+                                  int stride, int pad, int out_h, int out_w, int k_pad, void *stream) {
+  if (!src || !dst || batch <= 0 || channels <= 0 || k <= 0 || stride <= 0 || k_pad < k * k * channels)
+    return PCODEC_ERR_BAD_ARG;
+  const int64_t total = (int64_t)batch * out_h * out_w * k_pad;
+  im2col_nchw_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
+      src, dst, channels, height, width, k, stride, pad, out_h, out_w, k_pad, total);
+  PCODEC_RETURN_LAUNCH();
+}

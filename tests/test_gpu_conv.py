@@ -1,0 +1,189 @@
+"""Tap-GEMM convolution, GDN, pixel shuffle, attention kernels vs plain PyTorch fp32 (CPU) references."""
+import math
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-5  # fp32 accumulation-order noise, relative to the output's RMS
+
+
+def _engine(impl=0):
+    from progressivecodec_b200.engine import Engine
+
+    return Engine(torch.device("cuda", 0), impl)
+
+
+def _nhwc(x):
+    from progressivecodec_b200.engine import Act
+
+    return Act(x.permute(0, 2, 3, 1).contiguous().cuda())
+
+
+def _nchw(a):
+    return a.t[..., a.c0:a.c0 + a.C].permute(0, 3, 1, 2).cpu()
+
+
+def _close(got, ref, rtol=RTOL):
+    scale = ref.pow(2).mean().sqrt().item() + 1e-12
+    err = (got - ref).abs().max().item()
+    assert err <= rtol * scale * 8, (err, scale)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,hw", [(192, 192, 5, 2, (32, 48)), (192, 320, 5, 2, (16, 24)),
+                                                   (96, 96, 3, 1, (16, 24)), (192, 96, 1, 1, (9, 7)),
+                                                   (288, 256, 3, 2, (8, 12)), (64, 32, 3, 1, (32, 48)),
+                                                   (224, 176, 3, 1, (5, 11)), (320, 640, 5, 2, (8, 8))])
+def test_conv2d(cin, cout, k, stride, hw):
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import pack_conv2d
+
+    E = _engine()
+    torch.manual_seed(cin + cout + k)
+    m = nn.Conv2d(cin, cout, k, stride, k // 2)
+    x = torch.randn(2, cin, *hw)
+    ref = m(x).detach()
+    pc = pack_conv2d(m, E.device, "t")
+    _close(_nchw(E.conv_new(pc, [_nhwc(x)])), ref)
+    _close(_nchw(E.conv_new(pc, [_nhwc(x)], L.EPI_GELU)), F.gelu(ref))
+
+
+def test_first_conv_via_im2col():
+    from progressivecodec_b200.engine import pack_first_conv_im2col
+
+    E = _engine()
+    torch.manual_seed(0)
+    m = nn.Conv2d(3, 192, 5, 2, 2)
+    x = torch.rand(2, 3, 64, 128)
+    pc = pack_first_conv_im2col(m, E.device, 80, "c0")
+    got = E.conv_new(pc, [E.im2col_first(x.cuda(), 5, 2, 2, 80)])
+    _close(_nchw(got), m(x).detach())
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(320, 192, (4, 6)), (192, 192, (16, 24)), (192, 3, (32, 48))])
+def test_deconv_phases(cin, cout, hw):
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import pack_deconv_phases
+
+    E = _engine()
+    torch.manual_seed(cin)
+    m = nn.ConvTranspose2d(cin, cout, 5, 2, 2, 1)
+    x = torch.randn(2, cin, *hw)
+    ref = m(x).detach()
+    ph = pack_deconv_phases(m, E.device, "d")
+    _close(_nchw(E.deconv_new(ph, _nhwc(x))), ref)
+    _close(_nchw(E.deconv_new(ph, _nhwc(x), L.EPI_CLAMP01)), ref.clamp(0, 1))
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn(inverse):
+    from progressivecodec_b200.engine import pack_gdn
+    from progressivecodec_b200.layers import GDN
+    from progressivecodec_b200.synthetic import synthetic_tensor
+
+    E = _engine()
+    g = GDN(192, inverse=inverse)
+    with torch.no_grad():
+        g.beta.copy_(synthetic_tensor("g.beta", g.beta, 0))
+        g.gamma.copy_(synthetic_tensor("g.gamma", g.gamma, 0))
+    x = torch.randn(2, 192, 12, 20)
+    beta, gamma = g.effective()
+    norm = F.conv2d(x * x, gamma.reshape(192, 192, 1, 1), beta)
+    ref = x * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
+    _close(_nchw(E.gdn_new(pack_gdn(g, E.device, "g"), _nhwc(x), inverse)), ref)
+
+
+def test_subpel_conv_pixel_shuffle():
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import pack_conv2d
+
+    E = _engine()
+    torch.manual_seed(3)
+    m = nn.Conv2d(192, 224 * 4, 3, 1, 1)
+    x = torch.randn(2, 192, 4, 6)
+    ref = F.gelu(F.pixel_shuffle(m(x), 2)).detach()
+    _close(_nchw(E.conv_shuffle_new(pack_conv2d(m, E.device, "s"), _nhwc(x), L.EPI_GELU)), ref)
+
+
+def test_virtual_concat_and_epilogues():
+    """Segments from different tensors / channel windows == torch.cat; ADD_GELU / GATE / LRP epilogues; strided output."""
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import Act, new_act, pack_conv2d
+
+    E = _engine()
+    torch.manual_seed(4)
+    lm = torch.randn(2, 640, 8, 12)
+    yb = torch.randn(2, 320, 8, 12)
+    yp = torch.randn(2, 32, 8, 12)
+    m = nn.Conv2d(320 + 96 + 32, 224, 3, 1, 1)
+    cat = torch.cat([lm[:, 320:], yb[:, 64:160], yp], 1)
+    ref = m(cat).detach()
+    segs = [_nhwc(lm).slice(320, 320), _nhwc(yb).slice(64, 96), _nhwc(yp)]
+    pc = pack_conv2d(m, E.device, "cat")
+    _close(_nchw(E.conv_new(pc, segs)), ref)
+    # epilogues on a 32-channel output written into a channel window of a wider buffer
+    m2 = nn.Conv2d(64, 32, 3, 1, 1)
+    h = torch.randn(2, 64, 8, 12)
+    r1, r2 = torch.randn(2, 32, 8, 12), torch.randn(2, 32, 8, 12)
+    acc = m2(h).detach()
+    pc2 = pack_conv2d(m2, E.device, "e")
+    buf = new_act(2, 8, 12, 320, E.device)
+    buf.t.fill_(7.0)
+    for epi, ref2 in ((L.EPI_ADD, acc + r1), (L.EPI_ADD_GELU, F.gelu(acc + r1)),
+                      (L.EPI_GATE, r2 * torch.sigmoid(acc) + r1), (L.EPI_LRP, r1 + 0.5 * torch.tanh(acc) + r2)):
+        out = buf.slice(96, 32)
+        E.conv(pc2, [_nhwc(h)], out, epi, r1=_nhwc(r1), r2=_nhwc(r2))
+        _close(_nchw(out), ref2)
+        assert (buf.t[..., :96] == 7.0).all() and (buf.t[..., 128:] == 7.0).all()
+    out = new_act(2, 8, 12, 32, E.device)
+    E.conv(pc2, [_nhwc(h)], out, L.EPI_LRP, r1=_nhwc(r1))
+    _close(_nchw(out), r1 + 0.5 * torch.tanh(acc))
+
+
+def test_conv_is_batch_invariant_and_deterministic():
+    """Encoder and decoder must reproduce each other's mu/sigma bit for bit, whatever the batch size."""
+    from progressivecodec_b200.engine import pack_conv2d
+
+    E = _engine()
+    torch.manual_seed(5)
+    m = nn.Conv2d(352, 224, 3, 1, 1)
+    x = torch.randn(5, 352, 32, 48)
+    pc = pack_conv2d(m, E.device, "b")
+    full = _nchw(E.conv_new(pc, [_nhwc(x)]))
+    again = _nchw(E.conv_new(pc, [_nhwc(x)]))
+    assert torch.equal(full, again)
+    for b in (0, 3, 4):
+        one = _nchw(E.conv_new(pc, [_nhwc(x[b:b + 1])]))
+        assert torch.equal(one[0], full[b])
+
+
+@pytest.mark.parametrize("dim,ws,shift,hw", [(192, 8, 4, (16, 32)), (320, 4, 2, (8, 12)), (640, 4, 2, (4, 8)),
+                                              (192, 8, 0, (8, 8))])
+def test_window_attention_block(dim, ws, shift, hw):
+    """Full WinBasedAttention (qkv -> shifted-window attention -> proj -> +x) vs the oracle restatement."""
+    from conftest import build_pair
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import pack_linear
+    from progressivecodec_b200.layers import WinBasedAttention
+    from progressivecodec_b200.synthetic import synthetic_tensor
+    from oracle.codec_port import CodecConfig, OracleCodec
+
+    E = _engine()
+    torch.manual_seed(dim + ws)
+    m = WinBasedAttention(dim, 8, ws, shift)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            p.copy_(synthetic_tensor("blk." + n, p, 1))
+    sd = {"blk." + k: v for k, v in m.state_dict().items()}
+    orc = OracleCodec.__new__(OracleCodec)
+    orc.sd, orc._attn_mask_cache = sd, {}
+    x = torch.randn(2, dim, *hw)
+    ref = orc.win_attention(x, "blk", 8, ws, shift)
+    xa = _nhwc(x)
+    qkv = E.conv_new(pack_linear(m.attn.qkv, E.device, "qkv"), [xa])
+    att = E.window_attention(qkv, m.attn.bias_matrix().cuda().contiguous(), 8, ws, shift)
+    out = E.conv_new(pack_linear(m.attn.proj, E.device, "proj"), [att], L.EPI_ADD, r1=xa)
+    _close(_nchw(out), ref, rtol=5e-5)
