@@ -404,6 +404,9 @@ class ChannelProgresssiveWACNN(nn.Module):
         state = state if state is not None else {}
         mu_total: List[Act] = state.setdefault("mu_total", [])
         std_total: List[Act] = state.setdefault("std_total", [])
+        if self.all_scalable:  # per-pass pools so that consecutive list entries are adjacent channel ranges
+            mu_pool = new_act(B, h, w, 32 * n_prog, E.device)
+            sc_pool = new_act(B, h, w, 32 * n_prog, E.device)
         kind, q = ChannelMask.mode_for(mask_pol, quality)
         mask_mode = {"ones": L.MASK_ONES, "zeros": L.MASK_ZEROS, "threshold": L.MASK_THRESHOLD}[kind]
         sps = self.support_progressive_slices
@@ -420,7 +423,10 @@ class ChannelProgresssiveWACNN(nn.Module):
 
             mean_sup = self._merge_segments(E, [lm1] + support(not self.all_scalable, mu_total))
             scale_sup = self._merge_segments(E, [ls1] + support(not self.all_scalable, std_total))
-            mu, scale = new_act(B, h, w, 32, E.device), new_act(B, h, w, 32, E.device)
+            if self.all_scalable:
+                mu, scale = mu_pool.slice(32 * i, 32), sc_pool.slice(32 * i, 32)
+            else:
+                mu, scale = new_act(B, h, w, 32, E.device), new_act(B, h, w, 32, E.device)
             self._stack(E, P["cc_mean_transforms_prog"][i], mean_sup, mu)
             self._stack(E, P["cc_scale_transforms_prog"][i], scale_sup, scale)
             if self.all_scalable:  # bookkeeping only matters when the supports read these lists
@@ -443,9 +449,11 @@ class ChannelProgresssiveWACNN(nn.Module):
             out_i = y_hat_q.slice(32 * i, 32)
             if residual_before_lrp:  # forward_single_quality only (CHProg_cnn.py:1153-1164)
                 y_pre = Act((y_pre.dense() + base_i.dense()).contiguous())
-                self._stack(E, P["lrp_transforms_prog"][i], mean_sup + [y_pre], out_i, L.EPI_LRP, r1=y_pre)
+                self._stack(E, P["lrp_transforms_prog"][i], self._merge_segments(E, mean_sup + [y_pre]), out_i,
+                            L.EPI_LRP, r1=y_pre)
             else:
-                self._stack(E, P["lrp_transforms_prog"][i], mean_sup + [y_pre], out_i, L.EPI_LRP, r1=y_pre, r2=base_i)
+                self._stack(E, P["lrp_transforms_prog"][i], self._merge_segments(E, mean_sup + [y_pre]), out_i,
+                            L.EPI_LRP, r1=y_pre, r2=base_i)
         return y_hat_q
 
     # ------------------------------------------------------------------------------------------------------
@@ -577,8 +585,10 @@ class ChannelProgresssiveWACNN(nn.Module):
                 "mu_base": cat_nchw(mu_b), "mu": cat_nchw(mu_p), "std_base": cat_nchw(std_b), "std": cat_nchw(std_p)}
 
     @torch.no_grad()
-    def compress(self, x, quality=0.0, mask_pol=None, cust_map=None, return_device_streams: bool = False):
-        """CHProg_cnn.py:686-847.  One batched rANS launch codes every (slice, image) stream."""
+    def compress(self, x, quality=0.0, mask_pol=None, cust_map=None, return_device_streams: bool = False,
+                 debug: Optional[dict] = None):
+        """CHProg_cnn.py:686-847.  One batched rANS launch codes every (slice, image) stream.
+        `debug` (tests only) receives the device symbol / index planes [n_slices, B, 32*h*w] and z symbols."""
         if cust_map is not None:
             raise NotImplementedError("cust_map (gradient-derived custom masks) is outside the hot path (SURVEY.md §8f)")
         mask_pol = self.mask_policy if mask_pol is None else mask_pol
@@ -608,6 +618,8 @@ class ChannelProgresssiveWACNN(nn.Module):
                 masks.append(m)
 
             self._prog_slices(P, lm, ls, y_hat_base, quality, mask_pol, code_prog, "codec")
+        if debug is not None:
+            debug.update(symbols=sym, indexes=idx, z_symbols=z_sym, y=E.to_nchw(y), y_hat_base=E.to_nchw(y_hat_base))
         z_data, z_off = _ans.encode_batch(z_sym, z_idx, P["eb_tables"])
         y_data, y_off = _ans.encode_batch(sym.reshape(n_slices * B, n), idx.reshape(n_slices * B, n), P["gc_tables"])
         shape = torch.Size([z.H, z.W])
