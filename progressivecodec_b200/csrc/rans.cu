@@ -19,6 +19,19 @@ constexpr int kWarpsPerBlock = 1;  // one stream per CTA keeps few streams sprea
 // ------------------------------------------------------------------------------------------------
 // encoder
 // ------------------------------------------------------------------------------------------------
+// Division-free state update (Alverson reciprocals, as rans64.h's Rans64EncSymbol does on the CPU): for
+// 2 <= freq < 2^16, shift = ceil(log2 freq), rcp = ceil(2^(shift+63) / freq); then for every x < 2^63
+//   x / freq == mulhi64(x, rcp) >> (shift - 1)           (exact)
+// and C(s,x) = ((x/freq) << 16) + x % freq + start = x + start + (x/freq) * (65536 - freq).
+// The 64K-entry reciprocal table lives in global memory (512 KB, L2 resident) and is filled once per process.
+__device__ uint64_t g_rcp_table[65536];
+
+__global__ void rans_build_rcp_kernel() {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= 65536) return;
+  g_rcp_table[f] = rcp_for(f);
+}
+
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 rans_encode_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int n_streams,
                    int64_t n, const int32_t *__restrict__ cdfs, int cdf_stride,
@@ -45,22 +58,32 @@ rans_encode_kernel(const int32_t *__restrict__ symbols, const int32_t *__restric
   };
 
   const int64_t n_chunks = (n + 31) / 32;
-  for (int64_t c = n_chunks - 1; c >= 0; --c) {
+  // software pipeline: the symbol/index/table loads of chunk c-1 are issued before the serial walk of chunk c
+  uint32_t packed = 0, raw = 0;
+  uint64_t rcp = 0;
+  bool esc = false;
+  auto load_chunk = [&](int64_t c, uint32_t &packed_o, uint32_t &raw_o, uint64_t &rcp_o, bool &esc_o) {
     const int64_t i = c * 32 + lane;
-    const bool valid = i < n;
-    uint32_t packed = 0, raw = 0;
-    bool esc = false;
-    if (valid) {
+    packed_o = 0; raw_o = 0; rcp_o = 0; esc_o = false;
+    if (c >= 0 && i < n) {
       const int32_t t = __ldg(idx + i);
       const int32_t sy = __ldg(sym + i);
       const int32_t maxv = __ldg(cdf_sizes + t) - 2;
       int32_t slot;
-      classify(sy, __ldg(offsets + t), maxv, slot, raw, esc);
+      classify(sy, __ldg(offsets + t), maxv, slot, raw_o, esc_o);
       const int32_t *row = cdfs + (int64_t)t * cdf_stride;
       const uint32_t start = (uint32_t)__ldg(row + slot);
       const uint32_t freq = ((uint32_t)__ldg(row + slot + 1) - start) & 0xFFFFu;
-      packed = (start & 0xFFFFu) | (freq << 16);
+      packed_o = (start & 0xFFFFu) | (freq << 16);
+      rcp_o = g_rcp_table[freq];
     }
+  };
+  load_chunk(n_chunks - 1, packed, raw, rcp, esc);
+  for (int64_t c = n_chunks - 1; c >= 0; --c) {
+    uint32_t packed_n, raw_n;
+    uint64_t rcp_n;
+    bool esc_n;
+    load_chunk(c - 1, packed_n, raw_n, rcp_n, esc_n);
     const uint32_t esc_mask = __ballot_sync(0xFFFFFFFFu, esc);
     const int last = (int)min((int64_t)32, n - c * 32) - 1;
     for (int j = last; j >= 0; --j) {
@@ -75,8 +98,12 @@ rans_encode_kernel(const int32_t *__restrict__ symbols, const int32_t *__restric
           if (enc_put_bits4(x, kBypassMax, word)) emit(word);
       }
       const uint32_t p = __shfl_sync(0xFFFFFFFFu, packed, j);
-      if (enc_put(x, p & 0xFFFFu, p >> 16, word)) emit(word);
+      const uint64_t rc = __shfl_sync(0xFFFFFFFFu, rcp, j);
+      const uint32_t freq = p >> 16;
+      const uint32_t rshift = freq >= 2 ? (uint32_t)(31 - __clz(freq - 1)) : 0u;  // ceil(log2 freq) - 1
+      if (enc_put_rcp(x, p & 0xFFFFu, freq, rc, rshift, word)) emit(word);
     }
+    packed = packed_n; raw = raw_n; rcp = rcp_n; esc = esc_n;
   }
   // flush: low word first in memory (rans64.h:96-103)
   emit((uint32_t)(x >> 32));
@@ -144,110 +171,194 @@ rans_compact_kernel(const uint32_t *__restrict__ scratch, int64_t scratch_words,
 // ------------------------------------------------------------------------------------------------
 // decoder
 // ------------------------------------------------------------------------------------------------
-struct WordReader {
+// Decoder CTA = 3 warps per stream:
+//   warps 0,1 (producers) turn the known CDF indexes of the NEXT 32 symbols into shared-memory probe windows:
+//          for symbol j, lane l gets (start | freq << 16) of slot ws_j + l, where the 32-slot window is centred
+//          on the mode of that symbol's table.  None of this depends on the coder state.
+//   warp 2 (walker) runs the serial state chain from shared memory only.  Every lane evaluates the complete
+//          state update (multiply, renormalise with the speculatively fetched next word) for "its" candidate
+//          slot while it tests whether the slot contains the state's low 16 bits; exactly one lane is right and
+//          its 63-bit result is broadcast with two warp OR-reductions (redux.sync).  Bit 63 flags the rare
+//          events (word consumed / escape symbol); "no lane right" (symbol outside the window) shows as 0.
+//          The common path therefore has a single, normally not-taken branch per symbol.
+struct DecChunk {
+  uint32_t packed[32][32];  // [symbol j][lane]: start | freq << 16 of slot ws_j + lane (0xFFFF = no slot)
+  int32_t t[32], size[32], off[32], ws[32];
+};
+
+struct WordReader {  // walker-side: lane l caches word[cache_base + l]; `nw` is the next unread word (uniform)
   const uint32_t *base;
-  int64_t n_words;
-  int64_t rp;          // next word to read
-  int64_t cache_base;  // lane l caches word[cache_base + l]
-  uint32_t cache;
+  int32_t n_words, rp, cache_base;
+  uint32_t cache, nw;
   int lane;
-  __device__ __forceinline__ void fill(int64_t from) {
+  __device__ __forceinline__ void fill(int32_t from) {
     cache_base = from;
-    const int64_t i = from + lane;
+    const int32_t i = from + lane;
     cache = i < n_words ? __ldg(base + i) : 0u;
   }
-  __device__ __forceinline__ uint32_t next() {
-    if (rp - cache_base >= 32) fill(rp);
-    const uint32_t w = __shfl_sync(0xFFFFFFFFu, cache, (int)(rp - cache_base));
+  __device__ __forceinline__ void init(const uint32_t *b, int32_t n, int l) {
+    base = b; n_words = n; lane = l; rp = 0;
+    fill(0);
+    nw = __shfl_sync(0xFFFFFFFFu, cache, 0);
+  }
+  __device__ __forceinline__ void consume() {  // warp-uniform
     ++rp;
+    if (rp - cache_base >= 32) fill(rp);
+    nw = __shfl_sync(0xFFFFFFFFu, cache, rp - cache_base);
+  }
+  __device__ __forceinline__ uint32_t next() {
+    const uint32_t w = nw;
+    consume();
     return w;
   }
 };
 
-__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+__device__ __forceinline__ int32_t dec_escape(uint64_t &x, WordReader &rd, int32_t maxv) {
+  uint32_t v;
+  if (dec_get_bits4(x, v)) x = (x << 32) | rd.next();
+  int32_t nb = (int32_t)v;
+  while (v == kBypassMax) {
+    if (dec_get_bits4(x, v)) x = (x << 32) | rd.next();
+    nb += (int32_t)v;
+  }
+  uint32_t raw = 0;
+  for (int k = 0; k < nb; ++k) {
+    if (dec_get_bits4(x, v)) x = (x << 32) | rd.next();
+    if (k < 8) raw |= v << (k * kBypassBits);
+  }
+  int32_t value = (int32_t)(raw >> 1);
+  if (raw & 1u) value = -value - 1; else value += maxv;
+  return value;
+}
+
+constexpr int kDecThreads = 96;
+
+__global__ void __launch_bounds__(kDecThreads)
 rans_decode_kernel(const uint8_t *__restrict__ in_bytes, const int64_t *__restrict__ in_offsets, int n_streams,
                    int64_t n, const int32_t *__restrict__ indexes, const int32_t *__restrict__ cdfs, int cdf_stride,
                    const int32_t *__restrict__ cdf_sizes, const int32_t *__restrict__ offsets,
                    int32_t *__restrict__ out_symbols) {
+  __shared__ DecChunk buf[2];
+  __shared__ int32_t s_val[32];
   const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (s >= n_streams) return;
+  const int role = threadIdx.x >> 5;  // 0,1 = producers (symbols 0-15 / 16-31 of a chunk), 2 = walker
+  const int s = blockIdx.x;
   const int32_t *idx = indexes + (int64_t)s * n;
   int32_t *out = out_symbols + (int64_t)s * n;
-  WordReader rd;
-  rd.base = reinterpret_cast<const uint32_t *>(in_bytes + in_offsets[s]);
-  rd.n_words = (in_offsets[s + 1] - in_offsets[s]) / 4;
-  rd.lane = lane;
-  rd.rp = 0;
-  rd.fill(0);
-  uint64_t x = (uint64_t)rd.next();
-  x |= (uint64_t)rd.next() << 32;
-
   const int64_t n_chunks = (n + 31) / 32;
-  for (int64_t c = 0; c < n_chunks; ++c) {
+
+  WordReader rd;
+  uint64_t x = 0;
+  if (role == 2) {
+    rd.init(reinterpret_cast<const uint32_t *>(in_bytes + in_offsets[s]),
+            (int32_t)((in_offsets[s + 1] - in_offsets[s]) / 4), lane);
+    x = (uint64_t)rd.next();
+    x |= (uint64_t)rd.next() << 32;
+  }
+
+  // producers prefetch the index / table-meta loads one chunk ahead of the window build
+  int32_t t_n = 0, size_n = 2, off_n = 0;
+  auto load_meta = [&](int64_t c) {
     const int64_t i = c * 32 + lane;
-    int32_t t_l = 0, size_l = 2, off_l = 0;
-    if (i < n) {
-      t_l = __ldg(idx + i);
-      size_l = __ldg(cdf_sizes + t_l);
-      off_l = __ldg(offsets + t_l);
+    t_n = 0; size_n = 2; off_n = 0;
+    if (c < n_chunks && i < n) {
+      t_n = __ldg(idx + i);
+      size_n = __ldg(cdf_sizes + t_n);
+      off_n = __ldg(offsets + t_n);
     }
-    int32_t my_value = 0;
-    const int count = (int)min((int64_t)32, n - c * 32);
-    for (int j = 0; j < count; ++j) {
-      const int32_t t = __shfl_sync(0xFFFFFFFFu, t_l, j);
-      const int32_t size = __shfl_sync(0xFFFFFFFFu, size_l, j);
-      const int32_t off = __shfl_sync(0xFFFFFFFFu, off_l, j);
-      const int32_t *row = cdfs + (int64_t)t * cdf_stride;
-      const uint32_t cf = (uint32_t)(x & 0xFFFFu);
-      // 32-wide probe window centred on the slot of symbol value 0 (slot = -offset)
-      int32_t ws = -off - 15;
-      ws = max(0, min(ws, size - 32));
-      const int32_t pos = ws + lane;
-      const uint32_t val = pos < size ? (uint32_t)__ldg(row + pos) : 0xFFFFFFFFu;
-      const uint32_t gt = __ballot_sync(0xFFFFFFFFu, val > cf);
-      int32_t slot;
-      uint32_t start, next;
-      const int first = __ffs(gt) - 1;  // -1 when no probe entry exceeds cf
-      if (first > 0 || (first == 0 && ws == 0)) {
-        // first == 0 with ws == 0 cannot happen for a valid CDF (cdf[0] = 0 <= cf); clamped for safety
-        slot = max(ws + first - 1, 0);
-        start = __shfl_sync(0xFFFFFFFFu, val, max(first - 1, 0));
-        next = __shfl_sync(0xFFFFFFFFu, val, first);
-      } else {
-        // outside the window: uniform binary search for the last entry <= cf
-        int32_t lo = (first == 0) ? 0 : ws + 31;       // cdf[lo] <= cf
-        int32_t hi = (first == 0) ? ws : size - 1;     // cdf[hi] > cf
-        while (hi - lo > 1) {
-          const int32_t mid = (lo + hi) >> 1;
-          if ((uint32_t)__ldg(row + mid) <= cf) lo = mid; else hi = mid;
+  };
+  if (role < 2) load_meta(0);
+
+  for (int64_t c = 0; c <= n_chunks; ++c) {
+    if (role < 2) {
+      if (c < n_chunks) {
+        DecChunk &d = buf[c & 1];
+        const int32_t t_l = t_n, size_l = size_n, off_l = off_n;
+        load_meta(c + 1);
+        const int32_t ws_l = max(0, min(-off_l - 15, size_l - 32));
+        if (role == 0) { d.t[lane] = t_l; d.size[lane] = size_l; d.off[lane] = off_l; d.ws[lane] = ws_l; }
+#pragma unroll 8
+        for (int jj = 0; jj < 16; ++jj) {
+          const int j = role * 16 + jj;
+          const int32_t t = __shfl_sync(0xFFFFFFFFu, t_l, j);
+          const int32_t size = __shfl_sync(0xFFFFFFFFu, size_l, j);
+          const int32_t ws = __shfl_sync(0xFFFFFFFFu, ws_l, j);
+          const int32_t *row = cdfs + (int64_t)t * cdf_stride;
+          const int32_t pos = ws + lane;
+          uint32_t pk = 0xFFFFu;  // start 0xFFFF, freq 0: can never contain a 16-bit cumulative frequency
+          if (pos + 1 < size) {
+            const uint32_t v = (uint32_t)__ldg(row + pos), v2 = (uint32_t)__ldg(row + pos + 1);
+            pk = (v & 0xFFFFu) | ((v2 - v) << 16);
+          }
+          d.packed[j][lane] = pk;
         }
-        slot = lo;
-        start = (uint32_t)__ldg(row + lo);
-        next = (uint32_t)__ldg(row + lo + 1);
       }
-      if (dec_advance(x, start, next - start)) x = (x << 32) | rd.next();
-      int32_t value = slot;
-      const int32_t maxv = size - 2;
-      if (slot == maxv) {  // escape (warp-uniform)
-        uint32_t v;
-        if (dec_get_bits4(x, v)) x = (x << 32) | rd.next();
-        int32_t nb = (int32_t)v;
-        while (v == kBypassMax) {
-          if (dec_get_bits4(x, v)) x = (x << 32) | rd.next();
-          nb += (int32_t)v;
+    } else if (c >= 1) {
+      const int64_t cc = c - 1;
+      const DecChunk &d = buf[cc & 1];
+      const int count = (int)min((int64_t)32, n - cc * 32);
+      const int32_t off_l = d.off[lane];
+      const int32_t base_l = d.ws[lane] + off_l;  // value = (winning lane) + ws + offset for the lane's own symbol
+      uint32_t esc_mask = 0;
+      uint32_t pk = d.packed[0][lane];
+#pragma unroll 4
+      for (int j = 0; j < count; ++j) {
+        const uint32_t pk_next = d.packed[min(j + 1, 31)][lane];
+        const uint32_t cf = (uint32_t)(x & 0xFFFFu);
+        const uint32_t st_l = pk & 0xFFFFu, fr_l = pk >> 16;
+        const uint32_t rel = cf - st_l;
+        const bool valid = rel < fr_l;
+        // candidate successor state of this lane's slot (Rans64DecAdvance + refill with the speculative word)
+        uint64_t xc = (uint64_t)fr_l * (x >> kPrecision) + rel;
+        const bool need_l = xc < kRansLower;
+        if (need_l) xc = (xc << 32) | rd.nw;
+        const bool rare_l = need_l || (st_l + fr_l) == 65536u;
+        uint32_t hi_l = (uint32_t)(xc >> 32) | (rare_l ? 0x80000000u : 0u);
+        if (valid) s_val[j] = lane;
+        const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, valid ? (uint32_t)xc : 0u);
+        const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, valid ? hi_l : 0u);
+        if (__builtin_expect((int32_t)hi >= 0 && (hi | lo) != 0u, 1)) {
+          x = ((uint64_t)hi << 32) | lo;  // common case: found in the window, no word consumed, not an escape
+        } else {
+          bool esc;
+          if ((hi | lo) != 0u) {
+            x = ((uint64_t)(hi & 0x7FFFFFFFu) << 32) | lo;
+            const uint32_t flags = __reduce_or_sync(0xFFFFFFFFu, valid ? ((need_l ? 1u : 0u) |
+                                                                           ((st_l + fr_l) == 65536u ? 2u : 0u)) : 0u);
+            if (flags & 1u) rd.consume();
+            esc = (flags & 2u) != 0u;
+          } else {
+            // symbol outside the 32-slot window: uniform binary search for the last CDF entry <= cf
+            const int32_t size = d.size[j], ws = d.ws[j];
+            const int32_t *row = cdfs + (int64_t)d.t[j] * cdf_stride;
+            const bool below = ws > 0 && (uint32_t)__ldg(row + ws) > cf;
+            int32_t lo_i = below ? 0 : ws;         // cdf[lo] <= cf
+            int32_t hi_i = below ? ws : size - 1;  // cdf[hi] > cf
+            while (hi_i - lo_i > 1) {
+              const int32_t mid = (lo_i + hi_i) >> 1;
+              if ((uint32_t)__ldg(row + mid) <= cf) lo_i = mid; else hi_i = mid;
+            }
+            const uint32_t start = (uint32_t)__ldg(row + lo_i);
+            const uint32_t freq = (uint32_t)__ldg(row + lo_i + 1) - start;
+            if (dec_advance(x, start, freq)) x = (x << 32) | rd.next();
+            esc = (start + freq) == 65536u;
+            if (lane == 0) s_val[j] = lo_i - ws;
+          }
+          if (esc) {  // the last real slot is the escape slot
+            const int32_t v = dec_escape(x, rd, d.size[j] - 2);
+            __syncwarp();
+            if (lane == 0) s_val[j] = v;
+            esc_mask |= 1u << j;
+          }
         }
-        uint32_t raw = 0;
-        for (int k = 0; k < nb; ++k) {
-          if (dec_get_bits4(x, v)) x = (x << 32) | rd.next();
-          if (k < 8) raw |= v << (k * kBypassBits);
-        }
-        value = (int32_t)(raw >> 1);
-        if (raw & 1u) value = -value - 1; else value += maxv;
+        pk = pk_next;
       }
-      if (lane == j) my_value = value + off;
+      __syncwarp();
+      const int64_t i = cc * 32 + lane;
+      if (i < n) out[i] = s_val[lane] + (((esc_mask >> lane) & 1u) ? off_l : base_l);
+      __syncwarp();
     }
-    if (i < n) out[i] = my_value;
+    __syncthreads();
   }
 }
 
@@ -264,6 +375,19 @@ extern "C" int pcodec_rans_encode_batch(const int32_t *symbols, const int32_t *i
       !status || (n_per_stream > 0 && (!symbols || !indexes)))
     return PCODEC_ERR_BAD_ARG;
   cudaStream_t st = as_stream(stream);
+  {
+    // one-time fill of the reciprocal table (per device); ordered before the encode on the same stream
+    static std::atomic<uint64_t> built_mask{0};
+    int dev = 0;
+    PCODEC_CHECK_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(built_mask.load() & bit)) {
+      rans_build_rcp_kernel<<<256, 256, 0, st>>>();
+      PCODEC_COUNT_LAUNCH();
+      PCODEC_CHECK_CUDA(cudaStreamSynchronize(st));
+      built_mask.fetch_or(bit);
+    }
+  }
   PCODEC_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
   const int blocks = (n_streams + kWarpsPerBlock - 1) / kWarpsPerBlock;
   rans_encode_kernel<<<blocks, 32 * kWarpsPerBlock, 0, st>>>(symbols, indexes, n_streams, n_per_stream, cdfs,
@@ -287,8 +411,7 @@ extern "C" int pcodec_rans_decode_batch(const uint8_t *in_bytes, const int64_t *
   if (n_streams <= 0 || n_per_stream < 0 || !in_bytes || !in_offsets) return PCODEC_ERR_BAD_ARG;
   if (n_per_stream == 0) return PCODEC_OK;
   if (!indexes || !out_symbols) return PCODEC_ERR_BAD_ARG;
-  const int blocks = (n_streams + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  rans_decode_kernel<<<blocks, 32 * kWarpsPerBlock, 0, as_stream(stream)>>>(
+  rans_decode_kernel<<<n_streams, kDecThreads, 0, as_stream(stream)>>>(
       in_bytes, in_offsets, n_streams, n_per_stream, indexes, cdfs, cdf_stride, cdf_sizes, offsets, out_symbols);
   PCODEC_RETURN_LAUNCH();
 }
@@ -322,7 +445,10 @@ extern "C" int64_t pcodec_selftest_rans_core_encode(const int32_t *symbols, cons
     }
     const uint32_t start = (uint32_t)row[slot];
     const uint32_t freq = ((uint32_t)row[slot + 1] - start) & 0xFFFFu;
-    if (enc_put(x, start & 0xFFFFu, freq, word)) { if (wpos <= 0) return -1; words[--wpos] = word; }
+    // alternate between the division and the reciprocal form: both must yield the oracle's bytes
+    const bool e = (i & 1) ? enc_put(x, start & 0xFFFFu, freq, word)
+                           : enc_put_rcp(x, start & 0xFFFFu, freq, rcp_for(freq), freq >= 2 ? rcp_shift_for(freq) : 0u, word);
+    if (e) { if (wpos <= 0) return -1; words[--wpos] = word; }
   }
   if (wpos < 2) return -1;
   words[--wpos] = (uint32_t)(x >> 32);

@@ -52,6 +52,37 @@ PC_HD bool enc_put(uint64_t &x, uint32_t start, uint32_t freq, uint32_t &word) {
   return emit;
 }
 
+// ---- division-free variant (Alverson reciprocal, cf. rans64.h Rans64EncSymbolInit/Rans64EncPutSymbol) ----
+// For 2 <= freq < 2^16: shift = ceil(log2 freq), rcp = ceil(2^(shift+63)/freq); then for every x < 2^63
+//   x / freq == mulhi64(x, rcp) >> (shift - 1), and C(s,x) = x + start + (x/freq) * (65536 - freq).
+PC_HD uint32_t rcp_shift_for(uint32_t freq) {  // ceil(log2 freq) - 1, freq >= 2
+  uint32_t shift = 0;
+  while (freq > (1u << shift)) ++shift;
+  return shift - 1;
+}
+PC_HD uint64_t rcp_for(uint32_t freq) {
+  if (freq < 2) return ~0ull;
+  const uint32_t shift = rcp_shift_for(freq) + 1;
+  const unsigned __int128 num = ((unsigned __int128)1 << (shift + 63)) + freq - 1;
+  return (uint64_t)(num / freq);
+}
+PC_HD uint64_t mulhi_u64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+PC_HD bool enc_put_rcp(uint64_t &x, uint32_t start, uint32_t freq, uint64_t rcp, uint32_t rshift, uint32_t &word) {
+  const uint64_t x_max = (uint64_t)freq << (31 - kPrecision + 32);
+  const bool emit = x >= x_max;
+  word = (uint32_t)x;
+  if (emit) x >>= 32;
+  const uint64_t q = freq >= 2 ? (mulhi_u64(x, rcp) >> rshift) : x;
+  x = x + start + q * (uint64_t)(65536u - freq);
+  return emit;
+}
+
 // Encoder: push one raw 4-bit value; rans_interface.cpp:60-78 (Rans64EncPutBits, nbits = 4).
 PC_HD bool enc_put_bits4(uint64_t &x, uint32_t val, uint32_t &word) {
   bool emit = false;
