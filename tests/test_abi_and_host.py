@@ -1,0 +1,123 @@
+"""C-ABI surface and host-side logic (no GPU compute)."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import CASE_KWARGS, GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from progressivecodec_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "pcodec_b200.h")).read()
+    declared = set(re.findall(r"\b(pcodec_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/pcodec_b200.h but not exported"
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert lib.pcodec_version() >= 100
+
+
+def test_conv_desc_layout_matches_header():
+    """ctypes mirror of pcodec_conv_desc must have the C struct's size (checked against a tiny compiled probe)."""
+    import ctypes
+    import subprocess
+    import tempfile
+
+    from progressivecodec_b200 import _lib
+
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "pcodec_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(pcodec_conv_desc), ' \
+          'offsetof(pcodec_conv_desc, weight), offsetof(pcodec_conv_desc, out), offsetof(pcodec_conv_desc, r2));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "p.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "p")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        size, o_w, o_out, o_r2 = map(int, subprocess.check_output([exe]).split())
+    D = _lib.ConvDesc
+    assert (ctypes.sizeof(D), D.weight.offset, D.out.offset, D.r2.offset) == (size, o_w, o_out, o_r2)
+
+
+@pytest.mark.parametrize("case", list(CASE_KWARGS))
+def test_state_dict_keys_match_reference(case):
+    from progressivecodec_b200 import ChannelProgresssiveWACNN
+
+    net = ChannelProgresssiveWACNN(**CASE_KWARGS[case])
+    net.update()
+    mine = {k: (tuple(v.shape), str(v.dtype)) for k, v in net.state_dict().items()}
+    ref = {}
+    for line in open(os.path.join(GOLDEN, f"{case}_state_dict_keys.txt")):
+        k, rest = line.rstrip("\n").split(" ", 1)
+        shape, dtype = rest.rsplit(" ", 1)
+        ref[k] = (eval(shape), dtype)
+    assert set(mine) == set(ref)
+    bad = {k: (mine[k], ref[k]) for k in ref if mine[k] != ref[k] and "entropy_bottleneck._" not in k}
+    assert not bad, bad
+
+
+def test_state_dict_round_trip_resizes_cdf_buffers():
+    from progressivecodec_b200 import ChannelProgresssiveWACNN, apply_synthetic_weights
+
+    a = ChannelProgresssiveWACNN(**CASE_KWARGS["authors"])
+    apply_synthetic_weights(a, 0)
+    a.update(force=True)
+    b = ChannelProgresssiveWACNN(**CASE_KWARGS["authors"])   # CDF buffers still empty (cnn.py:195-202 behaviour)
+    b.load_state_dict(a.state_dict())
+    for (k, v), (k2, v2) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert k == k2 and torch.equal(v, v2), k
+    assert b.update() is False  # tables came from the checkpoint
+
+
+def test_quality_and_mask_mode_logic():
+    from progressivecodec_b200 import ChannelProgresssiveWACNN
+    from progressivecodec_b200.layers import ChannelMask
+
+    net = ChannelProgresssiveWACNN(**CASE_KWARGS["authors"])
+    assert net.define_quality(None) == [0, 1]
+    assert net.define_quality([0, 5]) == [0, 5] and net.define_quality([2, 5]) == [0, 2, 5]
+    assert net.define_quality(3) == [3]
+    assert ChannelMask.mode_for("point-based-std", 0) == ("zeros", None)
+    assert ChannelMask.mode_for("point-based-std", 10) == ("ones", None)
+    assert ChannelMask.mode_for("point-based-std", 12) == ("ones", None)
+    kind, q = ChannelMask.mode_for("point-based-std", 2.5)
+    assert kind == "threshold" and q == 1.0 - 2.5 * 0.1
+    assert ChannelMask.mode_for("two-levels", 0)[0] == "zeros" and ChannelMask.mode_for("two-levels", 0.1)[0] == "ones"
+    assert ChannelMask.mode_for(None, 3)[0] == "ones"
+    with pytest.raises(NotImplementedError):
+        ChannelMask.mode_for("learnable-mask-gamma", 1)
+
+
+def test_no_cpu_fallback_and_error_behaviour():
+    from progressivecodec_b200 import ChannelProgresssiveWACNN, PcodecError, GaussianConditional
+
+    net = ChannelProgresssiveWACNN(**CASE_KWARGS["authors"]).eval()
+    net.update()
+    with pytest.raises(PcodecError):      # model on the CPU: refuse instead of silently running PyTorch
+        net.compress(torch.rand(1, 3, 64, 64), quality=0)
+    with pytest.raises(PcodecError):
+        net.forward(torch.rand(1, 3, 64, 64), quality=[0, 1], training=False)
+    gc = GaussianConditional(None)
+    with pytest.raises(ValueError, match="Uninitialized CDFs"):
+        gc.device_tables("cpu")
+    with pytest.raises(NotImplementedError):
+        ChannelProgresssiveWACNN(u_net_post=1)
+    with pytest.raises(NotImplementedError):
+        ChannelProgresssiveWACNN(mask_policy="learnable-mask-gamma")
+
+
+def test_synthetic_weights_are_name_keyed_and_deterministic():
+    from progressivecodec_b200 import ChannelProgresssiveWACNN, apply_synthetic_weights
+
+    a = ChannelProgresssiveWACNN(**CASE_KWARGS["authors"])
+    b = ChannelProgresssiveWACNN(**CASE_KWARGS["multienc"])
+    apply_synthetic_weights(a, 0)
+    apply_synthetic_weights(b, 0)
+    sa, sb = a.state_dict(), b.state_dict()
+    shared = [k for k in sa if k in sb and sa[k].shape == sb[k].shape and "entropy_bottleneck._" not in k
+              and "gaussian_conditional" not in k]
+    assert len(shared) > 500
+    for k in shared:
+        assert torch.equal(sa[k], sb[k]), k
