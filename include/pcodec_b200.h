@@ -190,10 +190,23 @@ typedef struct {
   int epilogue, flags;
   const float *r1; int r1_pixel_stride; /* indexed like `out` (same pixel, same channel) */
   const float *r2; int r2_pixel_stride;
+  /* tensor-core path: handle from pcodec_conv_tc_prepare for these weights (NULL = fp32 SIMT kernel only) and the
+   * number of TF32 products per MAC: 3 = split accumulation (fp32-class accuracy), 1 = plain TF32 */
+  const void *tc_weights;
+  int tc_split;
 } pcodec_conv_desc;
 
-/* HOST descriptor, DEVICE tensors.  impl: 0 = auto, 1 = fp32 SIMT, 2 = tcgen05 3xTF32 (error if the shape is unsupported). */
+/* HOST descriptor, DEVICE tensors.  impl: 0 = auto (tcgen05 when desc->tc_weights is set and the shape is supported,
+ * else SIMT), 1 = fp32 SIMT, 2 = tcgen05 (PCODEC_ERR_UNSUPPORTED if it cannot run this descriptor). */
 int pcodec_conv_taps(const pcodec_conv_desc *desc, int impl, void *stream);
+
+/* Prepare weights for the tcgen05 kernel: takes the SIMT layout [n_taps][cin_total][cout] (device), builds the
+ * K-major TF32 hi/lo copies [cout][n_taps*cin_total] and their TMA tensor maps; *handle_out is an opaque HOST handle
+ * to put in pcodec_conv_desc.tc_weights.  PCODEC_ERR_UNSUPPORTED when cout is not a multiple of 16 (e.g. the
+ * 3-channel output layer) or the driver lacks cuTensorMapEncodeTiled. */
+int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int cin_total, int cout, void **handle_out,
+                           void *stream);
+void pcodec_conv_tc_release(void *handle);
 
 /* ------------------------------------------------------------------------------------------
  * Shifted-window attention core (win_attention.py:84-115, 153-207)

@@ -39,6 +39,7 @@ class ConvDesc(C.Structure):
         ("epilogue", C.c_int), ("flags", C.c_int),
         ("r1", C.c_void_p), ("r1_pixel_stride", C.c_int),
         ("r2", C.c_void_p), ("r2_pixel_stride", C.c_int),
+        ("tc_weights", C.c_void_p), ("tc_split", C.c_int),
     ]
 
 
@@ -70,6 +71,8 @@ PROTOTYPES = {
     "pcodec_bottleneck_indexes": (_i, [_i, _i64, _i, _vp, _vp]),
     "pcodec_bottleneck_likelihood": (_i, [_vp, _i, _vp, _i, _i64, _i, _vp, _vp]),
     "pcodec_conv_taps": (_i, [C.POINTER(ConvDesc), _i, _vp]),
+    "pcodec_conv_tc_prepare": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_void_p), _vp]),
+    "pcodec_conv_tc_release": (None, [_vp]),
     "pcodec_window_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pcodec_im2col_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pcodec_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _vp]),

@@ -1,6 +1,547 @@
-// tcgen05 / TMA implicit-GEMM path (3xTF32 split accumulation) — see DESIGN.md.  Placeholder until the kernel
-// lands: reports "unsupported" so pcodec_conv_taps(impl=0) routes everything to the fp32 SIMT kernel.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution ("sum of shifted-tap GEMMs") with 3xTF32 split accumulation.
+//
+// Same contract as the SIMT kernel (conv_simt.cu) but the contraction runs on the 5th-gen tensor cores:
+//   * CTA tile 128 (output pixels) x BN (output channels, 16..256), K slab = 32 input channels of one tap.
+//   * B (weights, K-major [Cout][T*Cin] fp32, pre-split on the host into TF32 hi and lo parts) arrives by TMA
+//     (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage ring; OOB columns of the last slab are
+//     zero-filled by the TMA unit.
+//   * A (activations) is an on-the-fly gather of the shifted NHWC patch (padding / stride / virtual concat /
+//     x*x for GDN handled in the address math), so four producer warps load it with coalesced 128-bit LDGs, split
+//     every value into hi = tf32 part and lo = x - hi, and store both in the canonical SWIZZLE_128B K-major
+//     layout the UMMA descriptors expect (16-byte chunk index XOR (row & 7)).
+//   * One elected thread issues tcgen05.mma.kind::tf32: acc += Ahi*Bhi + Alo*Bhi + Ahi*Blo (fp32 accumulator in
+//     TMEM). The dropped Alo*Blo term is ~2^-22 relative, i.e. fp32-class accuracy, which the codec needs because
+//     these outputs feed round(), sigma->CDF-index thresholds and the quantile ranking.
+//     `tc_split = 1` issues only the first product (plain TF32) — used for the synthesis transform g_s, whose
+//     output only enters PSNR.
+//   * tcgen05.commit releases ring slots and finally signals the epilogue; the producer warps then read the
+//     accumulator with tcgen05.ld (one TMEM lane = one output pixel per thread), apply the fused epilogue
+//     (bias / GELU / residual / gate / GDN / LRP / clamp / pixel-shuffle) and store 64-byte runs per thread.
+// The K order (segment, tap, channel slab; hi*hi, lo*hi, hi*lo) is fixed: deterministic and batch invariant.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
 
-bool pcodec_conv_taps_tc_supported(const pcodec_conv_desc *) { return false; }
-int pcodec_conv_taps_tc(const pcodec_conv_desc *, void *) { return PCODEC_ERR_UNSUPPORTED; }
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                  // fp32 elements per K slab = 128 bytes = one swizzle row
+constexpr int TC_A_BYTES = TC_BM * 128;    // one A tile (hi or lo)
+constexpr int TC_THREADS = 192;            // warps 0-3: A producers + epilogue, warp 4: TMA + TMEM alloc, warp 5: MMA
+constexpr int TC_SMEM_LIMIT = 220 * 1024;
+
+struct TcWeights {
+  CUtensorMap map_hi, map_lo;
+  float *dev_hi, *dev_lo;  // [cout][k_total]
+  int cout, k_total, bn, n_tiles;
+};
+
+struct TcParams {
+  pcodec_conv_desc d;
+  int64_t M;
+  int bn, stages, split, n_steps;
+  int n_hi_acc;  // TMEM accumulators for the hi*hi products (round-robin over K slabs); +1 for the lo terms when split
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"(0x989680)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, M=128, N from idesc, K=8
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// SWIZZLE_128B, K-major, 8-row x 128-byte atoms stacked along M/N with a 1024-byte stride (SM100 descriptor v1)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)0 << 16;                       // leading byte offset (unused: one swizzle atom along K)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // layout type: SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ float tc_epilogue(int epi, float acc, float r1, float r2, bool has_r2) {
+  switch (epi) {
+    case PCODEC_EPI_GELU: return gelu_erf(acc);
+    case PCODEC_EPI_ADD: return acc + r1;
+    case PCODEC_EPI_ADD_GELU: return gelu_erf(acc + r1);
+    case PCODEC_EPI_GATE: return r2 * sigmoid_f(acc) + r1;
+    case PCODEC_EPI_GDN: return r1 * rsqrtf(acc);
+    case PCODEC_EPI_IGDN: return r1 * sqrtf(acc);
+    case PCODEC_EPI_LRP: {
+      float v = __fadd_rn(r1, __fmul_rn(0.5f, tanhf(acc)));
+      return has_r2 ? __fadd_rn(v, r2) : v;
+    }
+    case PCODEC_EPI_CLAMP01: return fminf(fmaxf(acc, 0.f), 1.f);
+    default: return acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap map_hi,
+                    const __grid_constant__ CUtensorMap map_lo) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const pcodec_conv_desc &d = P.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = P.bn, stages = P.stages;
+  const bool split = P.split == 3;
+  const int b_bytes = bn * 128;
+  const int stage_bytes = (split ? 2 : 1) * (TC_A_BYTES + b_bytes);
+
+  // 1024-byte aligned carve-up
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto a_hi = [&](int s) { return smem_base + s * stage_bytes; };
+  auto a_lo = [&](int s) { return smem_base + s * stage_bytes + TC_A_BYTES; };
+  auto b_hi = [&](int s) { return smem_base + s * stage_bytes + (split ? 2 : 1) * TC_A_BYTES; };
+  auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
+  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto full_b = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto empty = [&](int s) { return bar_base + 8u * (2 * stages + s); };
+  const uint32_t tmem_full = bar_base + 8u * (3 * stages);
+  const uint32_t tmem_slot = tmem_full + 8u;
+  uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
+
+  // TMEM accumulators: the tensor core's fp32 accumulate truncates (round-toward-zero) once per MMA, so the error
+  // grows linearly with the number of MMAs that touch an accumulator.  The small lo*hi / hi*lo products therefore
+  // get their own accumulator (their truncation error is 2^-11 smaller in absolute terms), and the hi*hi
+  // products round-robin over n_hi_acc accumulators; the epilogue sums them with round-to-nearest adds.
+  const int n_acc = P.n_hi_acc + (split ? 1 : 0);
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < n_acc * bn) tmem_cols <<= 1;
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_a(s), 128);
+      mbar_init(full_b(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+
+  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * bn;
+  const int n_steps = P.n_steps;
+
+  if (warp < 4) {
+    // =============================== A producers ===============================
+    const int chunk = lane & 7;  // 16-byte chunk inside the 128-byte slab row
+    const int sub = lane >> 3;
+    int64_t pix_base[8];
+    int ih0[8], iw0[8];
+    bool ok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = warp * 32 + i * 4 + sub;
+      const int64_t m = m0 + row;
+      ok[i] = m < P.M;
+      const int64_t mm = ok[i] ? m : 0;
+      const int w = (int)(mm % d.grid_w);
+      const int64_t t = mm / d.grid_w;
+      const int h = (int)(t % d.grid_h);
+      const int64_t n = t / d.grid_h;
+      pix_base[i] = n * d.in_h * (int64_t)d.in_w;
+      ih0[i] = h * d.in_step;
+      iw0[i] = w * d.in_step;
+    }
+    const bool square = (d.flags & PCODEC_FLAG_SQUARE_INPUT) != 0;
+    int seg = 0, tap = 0, kc = 0;  // kc: 32-channel slab inside the segment
+    float4 cur[8], nxt[8];
+    auto fetch = [&](float4 (&v)[8]) {
+      const pcodec_segment &sg = d.seg[seg];
+      const int dy = d.dy[tap], dx = d.dx[tap];
+      const int c = kc * TC_BK + chunk * 4;
+      const bool c_ok = c < sg.channels;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int iy = ih0[i] + dy, ix = iw0[i] + dx;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[i] && c_ok && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w)
+          x = __ldg(reinterpret_cast<const float4 *>(sg.ptr + (pix_base[i] + (int64_t)iy * d.in_w + ix) * sg.pixel_stride + c));
+        v[i] = x;
+      }
+      if (++kc == (sg.channels + TC_BK - 1) / TC_BK) {
+        kc = 0;
+        if (++tap == d.n_taps) { tap = 0; ++seg; }
+      }
+    };
+    fetch(nxt);
+    for (int s = 0; s < n_steps; ++s) {
+      const int st = s % stages;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      if (s + 1 < n_steps) fetch(nxt);
+      mbar_wait(empty(st), ((s / stages) & 1) ^ 1);
+      uint8_t *hi_base = smem_gen + (a_hi(st) - smem_base);
+      uint8_t *lo_base = smem_gen + (a_lo(st) - smem_base);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = warp * 32 + i * 4 + sub;
+        const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
+        float4 x = cur[i];
+        if (square) { x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w; }
+        if (split) {
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+          *reinterpret_cast<float4 *>(hi_base + off) = h;
+          *reinterpret_cast<float4 *>(lo_base + off) = l;
+        } else {
+          *reinterpret_cast<float4 *>(hi_base + off) = x;
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(full_a(st));
+    }
+
+    // =============================== epilogue ===============================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;  // TMEM lane == tile row
+    const int64_t m = m0 + row;
+    const bool row_ok = m < P.M;
+    const int64_t mm = row_ok ? m : 0;
+    const int w = (int)(mm % d.grid_w);
+    const int64_t t = mm / d.grid_w;
+    const int h = (int)(t % d.grid_h);
+    const int64_t n = t / d.grid_h;
+    const int oh = h * d.out_step + d.out_off_y, ow = w * d.out_step + d.out_off_x;
+    const int64_t opix = (n * d.out_h + oh) * (int64_t)d.out_w + ow;
+    const bool shuffle = (d.flags & PCODEC_FLAG_PIXEL_SHUFFLE2) != 0;
+    const bool has_r2 = d.r2 != nullptr;
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < bn; c0 += 16) {
+      float acc[16];
+      tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective: executed by all lanes, stores are predicated
+      for (int a = 1; a < n_acc; ++a) {
+        float part[16];
+        tmem_ld16(lane_addr + (uint32_t)(a * bn + c0), part);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += part[j];
+      }
+      if (!row_ok) continue;
+      const int co0 = n0 + c0;
+      float bias[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bias[j] = d.bias ? __ldg(d.bias + co0 + j) : 0.f;
+      if (!shuffle) {
+        float r1[16], r2[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 a = d.r1 ? *reinterpret_cast<const float4 *>(d.r1 + opix * d.r1_pixel_stride + co0 + 4 * q)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 b = d.r2 ? *reinterpret_cast<const float4 *>(d.r2 + opix * d.r2_pixel_stride + co0 + 4 * q)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          r1[4 * q] = a.x; r1[4 * q + 1] = a.y; r1[4 * q + 2] = a.z; r1[4 * q + 3] = a.w;
+          r2[4 * q] = b.x; r2[4 * q + 1] = b.y; r2[4 * q + 2] = b.z; r2[4 * q + 3] = b.w;
+        }
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = tc_epilogue(d.epilogue, acc[j] + bias[j], r1[j], r2[j], has_r2);
+        float *dst = d.out + opix * d.out_pixel_stride + co0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = co0 + j;
+          const float v = tc_epilogue(d.epilogue, acc[j] + bias[j], 0.f, 0.f, false);
+          const int c = co >> 2, si = (co >> 1) & 1, sj = co & 1;
+          const int64_t sp = (n * d.out_h + (2 * oh + si)) * (int64_t)d.out_w + (2 * ow + sj);
+          d.out[sp * d.out_pixel_stride + c] = v;
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =============================== TMA producer for B ===============================
+    if (lane == 0) {
+      int seg = 0, tap = 0, kc = 0, seg_cbase = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s % stages;
+        mbar_wait(empty(st), ((s / stages) & 1) ^ 1);
+        const int k = tap * d.cin_total + seg_cbase + kc * TC_BK;
+        mbar_expect_tx(full_b(st), (uint32_t)((split ? 2 : 1) * b_bytes));
+        tma_load_2d(b_hi(st), &map_hi, full_b(st), k, n0);
+        if (split) tma_load_2d(b_lo(st), &map_lo, full_b(st), k, n0);
+        const int sc = d.seg[seg].channels;
+        if (++kc == (sc + TC_BK - 1) / TC_BK) {
+          kc = 0;
+          if (++tap == d.n_taps) { tap = 0; seg_cbase += sc; ++seg; }
+        }
+      }
+    }
+  } else {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s % stages;
+        const uint32_t ph = (s / stages) & 1;
+        mbar_wait(full_a(st), ph);
+        mbar_wait(full_b(st), ph);
+        tc_fence_after();
+        const uint64_t da_hi = umma_desc_sw128(a_hi(st)), db_hi = umma_desc_sw128(b_hi(st));
+        const uint64_t da_lo = umma_desc_sw128(a_lo(st)), db_lo = umma_desc_sw128(b_lo(st));
+        const int hi_idx = s % P.n_hi_acc;
+        const uint32_t acc_hi = tmem_acc + (uint32_t)(hi_idx * bn);
+        const uint32_t acc_lo = tmem_acc + (uint32_t)(P.n_hi_acc * bn);
+        const bool first_hi = s < P.n_hi_acc;  // first slab that touches this hi accumulator
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);  // 8 tf32 = 32 bytes = 2 x 16-byte units inside the swizzle row
+          umma_tf32(acc_hi, da_hi + adv, db_hi + adv, idesc, (!first_hi || k > 0) ? 1u : 0u);
+          if (split) {
+            umma_tf32(acc_lo, da_lo + adv, db_hi + adv, idesc, (s > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(acc_lo, da_hi + adv, db_lo + adv, idesc, 1u);
+          }
+        }
+        umma_commit(empty(st));  // implies tcgen05.fence::before_thread_sync
+      }
+      umma_commit(tmem_full);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+__global__ void split_weights_kernel(const float *__restrict__ w_tap_major, int n_taps, int cin, int cout,
+                                     float *__restrict__ hi, float *__restrict__ lo) {
+  // in: [tap][cin][cout]; out: [cout][tap*cin + ci] as TF32 hi (round to nearest even) and lo = w - hi
+  const int64_t total = (int64_t)n_taps * cin * cout;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = (int)(i % ((int64_t)n_taps * cin));
+  const int co = (int)(i / ((int64_t)n_taps * cin));
+  const float w = w_tap_major[(int64_t)k * cout + co];
+  uint32_t u = __float_as_uint(w);
+  u += 0x00000FFFu + ((u >> 13) & 1u);  // round to nearest even at bit 13
+  u &= 0xFFFFE000u;
+  const float h = __uint_as_float(u);
+  hi[i] = h;
+  lo[i] = w - h;
+}
+
+// N tile: the widest multiple of 16 that divides cout and fits the TMEM budget.  Long reductions (K >= 1024) get
+// a narrower tile (<= 128 columns) so that 3 hi accumulators + 1 lo accumulator fit in the 512 TMEM columns: the
+// tensor core truncates once per MMA per accumulator, so spreading the K slabs over more accumulators keeps the
+// result at fp32-class accuracy (measured: rms 1e-5 -> 3e-6 at K = 4800).
+int pick_bn(int cout, int k_total) {
+  if (cout % 16 != 0) return 0;
+  const int cap = k_total >= 1024 ? 128 : 256;
+  int fallback = 0;
+  for (int tiles = 1; tiles <= 16; ++tiles) {
+    if (cout % tiles) continue;
+    const int bn = cout / tiles;
+    if (bn % 16 != 0) continue;
+    if (bn <= 256 && fallback == 0) fallback = bn;
+    if (bn <= cap) return bn;
+  }
+  return fallback;
+}
+
+}  // namespace
+
+extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int cin_total, int cout, void **handle_out,
+                                      void *stream) {
+  if (!w_tap_major || !handle_out || n_taps < 1 || cin_total < 4 || cout < 1) return PCODEC_ERR_BAD_ARG;
+  *handle_out = nullptr;
+  const int bn = pick_bn(cout, n_taps * cin_total);
+  if (bn == 0 || (cin_total % 4) != 0) return PCODEC_ERR_UNSUPPORTED;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return PCODEC_ERR_UNSUPPORTED;
+  TcWeights *h = new TcWeights();
+  h->cout = cout;
+  h->k_total = n_taps * cin_total;
+  h->bn = bn;
+  h->n_tiles = cout / bn;
+  const size_t bytes = sizeof(float) * (size_t)cout * h->k_total;
+  if (cudaMalloc(&h->dev_hi, bytes) != cudaSuccess || cudaMalloc(&h->dev_lo, bytes) != cudaSuccess) {
+    delete h;
+    return -(int)cudaErrorMemoryAllocation;
+  }
+  const int64_t total = (int64_t)cout * h->k_total;
+  split_weights_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(w_tap_major, n_taps, cin_total,
+                                                                                       cout, h->dev_hi, h->dev_lo);
+  PCODEC_COUNT_LAUNCH();
+  const cuuint64_t dims[2] = {(cuuint64_t)h->k_total, (cuuint64_t)cout};
+  const cuuint64_t strides[1] = {(cuuint64_t)h->k_total * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+  const cuuint32_t estr[2] = {1, 1};
+  for (int part = 0; part < 2; ++part) {
+    CUresult r = enc(part == 0 ? &h->map_hi : &h->map_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     part == 0 ? (void *)h->dev_hi : (void *)h->dev_lo, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      cudaFree(h->dev_hi);
+      cudaFree(h->dev_lo);
+      delete h;
+      return PCODEC_ERR_UNSUPPORTED;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -(int)e;
+  *handle_out = h;
+  return PCODEC_OK;
+}
+
+extern "C" void pcodec_conv_tc_release(void *handle) {
+  if (!handle) return;
+  TcWeights *h = static_cast<TcWeights *>(handle);
+  cudaFree(h->dev_hi);
+  cudaFree(h->dev_lo);
+  delete h;
+}
+
+bool pcodec_conv_taps_tc_supported(const pcodec_conv_desc *d) {
+  if (!d->tc_weights) return false;
+  const TcWeights *h = static_cast<const TcWeights *>(d->tc_weights);
+  if (h->cout != d->cout || h->k_total != d->n_taps * d->cin_total) return false;
+  if (d->tc_split != 1 && d->tc_split != 3) return false;
+  // float4 epilogue accesses
+  if ((d->out_pixel_stride & 3) || (reinterpret_cast<uintptr_t>(d->out) & 15)) return false;
+  if (d->r1 && ((d->r1_pixel_stride & 3) || (reinterpret_cast<uintptr_t>(d->r1) & 15))) return false;
+  if (d->r2 && ((d->r2_pixel_stride & 3) || (reinterpret_cast<uintptr_t>(d->r2) & 15))) return false;
+  return true;
+}
+
+int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
+  const TcWeights *h = static_cast<const TcWeights *>(desc->tc_weights);
+  TcParams P;
+  P.d = *desc;
+  P.M = (int64_t)desc->batch * desc->grid_h * desc->grid_w;
+  P.bn = h->bn;
+  P.split = desc->tc_split;
+  int n_steps = 0;
+  for (int s = 0; s < desc->n_segments; ++s) n_steps += desc->n_taps * ((desc->seg[s].channels + TC_BK - 1) / TC_BK);
+  P.n_steps = n_steps;
+  const int stage_bytes = (P.split == 3 ? 2 : 1) * (TC_A_BYTES + h->bn * 128);
+  int stages = (TC_SMEM_LIMIT - 2048) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages > n_steps) stages = n_steps;
+  if (stages < 1) return PCODEC_ERR_UNSUPPORTED;
+  P.stages = stages;
+  {
+    int n_hi = 512 / h->bn - (P.split == 3 ? 1 : 0);
+    if (n_hi > 4) n_hi = 4;
+    if (n_hi > n_steps) n_hi = n_steps;
+    if (n_hi < 1) n_hi = 1;
+    P.n_hi_acc = n_hi;
+  }
+  const int smem = stages * stage_bytes + 1024 /*align*/ + 8 * (3 * stages + 2) + 64;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 4096);
+  });
+  if (attr_err != cudaSuccess) return -(int)attr_err;
+  dim3 grid((unsigned)ceil_div64(P.M, TC_BM), (unsigned)h->n_tiles);
+  conv_taps_tc_kernel<<<grid, TC_THREADS, smem, as_stream(stream)>>>(P, h->map_hi, h->map_lo);
+  PCODEC_RETURN_LAUNCH();
+}

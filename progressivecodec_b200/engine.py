@@ -50,7 +50,7 @@ def new_act(B: int, H: int, W: int, channels: int, device) -> Act:
 class PackedConv:
     """Weights of one tap-GEMM: fp32 [T][Cin][Cout] + bias + tap offsets."""
 
-    __slots__ = ("w", "bias", "taps", "cin", "cout", "in_step", "out_step", "off", "name")
+    __slots__ = ("w", "bias", "taps", "cin", "cout", "in_step", "out_step", "off", "name", "tc", "tc_split")
 
     def __init__(self, w: Tensor, bias: Optional[Tensor], taps: Sequence[Tuple[int, int]], in_step=1, out_step=1,
                  off=(0, 0), name=""):
@@ -61,6 +61,30 @@ class PackedConv:
         self.cin, self.cout = w.shape[1], w.shape[2]
         self.in_step, self.out_step, self.off = in_step, out_step, off
         self.name = name
+        self.tc = None       # opaque handle from pcodec_conv_tc_prepare (tcgen05 path)
+        self.tc_split = 3
+
+    def attach_tc(self, split: int = 3) -> "PackedConv":
+        """Build the TF32 hi/lo K-major weights + TMA maps for the tcgen05 kernel (no-op when unsupported,
+        e.g. the 3-channel output layer, which stays on the fp32 SIMT kernel)."""
+        if self.tc is None and self.w.is_cuda:
+            h = C.c_void_p()
+            rc = L.lib().pcodec_conv_tc_prepare(self.w.data_ptr(), len(self.taps), self.cin, self.cout, C.byref(h),
+                                                _stream())
+            if rc == L.OK:
+                self.tc = h.value
+            elif rc != L.ERR_UNSUPPORTED:
+                L.check(rc, f"conv_tc_prepare[{self.name}]")
+        self.tc_split = split
+        return self
+
+    def __del__(self):
+        try:
+            if self.tc is not None:
+                L.lib().pcodec_conv_tc_release(self.tc)
+                self.tc = None
+        except Exception:
+            pass
 
 
 def pack_conv2d(m: nn.Conv2d, device, name="") -> PackedConv:
@@ -170,6 +194,7 @@ class Engine:
             d.r1, d.r1_pixel_stride = r1.ptr, r1.ps
         if r2 is not None:
             d.r2, d.r2_pixel_stride = r2.ptr, r2.ps
+        d.tc_weights, d.tc_split = pc.tc, pc.tc_split
         L.check(self.lib.pcodec_conv_taps(C.byref(d), self.conv_impl, _stream()), f"conv_taps[{pc.name}]")
         return out
 

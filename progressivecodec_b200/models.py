@@ -131,6 +131,9 @@ class ChannelProgresssiveWACNN(nn.Module):
         self.entropy_bottleneck = EntropyBottleneck(N)
         self.gaussian_conditional = GaussianConditional(None)
         self._packed: Optional[dict] = None
+        # execution knobs (not part of the reference API): tcgen05 path on/off, TF32 products per MAC in g_s
+        self.tensor_cores = True
+        self.synthesis_tf32_passes = 3
 
     # ------------------------------------------------------------------------------------------------------
     # state handling
@@ -239,6 +242,20 @@ class ChannelProgresssiveWACNN(nn.Module):
         for fam in ("cc_mean_transforms", "cc_scale_transforms", "lrp_transforms", "cc_mean_transforms_prog",
                     "cc_scale_transforms_prog", "lrp_transforms_prog"):
             P[fam] = [stack(m, f"{fam}.{i}") for i, m in enumerate(getattr(self, fam))]
+        if self.tensor_cores:
+            def walk(o, split):
+                if isinstance(o, PackedConv):
+                    o.attach_tc(split)
+                elif isinstance(o, dict):
+                    for v in o.values():
+                        walk(v, split)
+                elif isinstance(o, (list, tuple)):
+                    for v in o:
+                        walk(v, split)
+            for key, val in P.items():
+                # g_s only feeds the reconstruction (PSNR): plain TF32; everything that feeds round(), the sigma
+                # thresholds or the quantile ranking uses the 3xTF32 split (fp32-class accuracy)
+                walk(val, self.synthesis_tf32_passes if key == "g_s" else 3)
         gc, eb = self.gaussian_conditional, self.entropy_bottleneck
         P["scale_table"] = gc.scale_table.detach().to(dev).float().contiguous()
         P["scale_bound"] = float(gc.scale_bound.item())

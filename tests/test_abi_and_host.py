@@ -30,7 +30,7 @@ def test_conv_desc_layout_matches_header():
     from progressivecodec_b200 import _lib
 
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "pcodec_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(pcodec_conv_desc), ' \
-          'offsetof(pcodec_conv_desc, weight), offsetof(pcodec_conv_desc, out), offsetof(pcodec_conv_desc, r2));return 0;}'
+          'offsetof(pcodec_conv_desc, weight), offsetof(pcodec_conv_desc, out), offsetof(pcodec_conv_desc, tc_split));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
         open(c, "w").write(src)
@@ -38,7 +38,7 @@ def test_conv_desc_layout_matches_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         size, o_w, o_out, o_r2 = map(int, subprocess.check_output([exe]).split())
     D = _lib.ConvDesc
-    assert (ctypes.sizeof(D), D.weight.offset, D.out.offset, D.r2.offset) == (size, o_w, o_out, o_r2)
+    assert (ctypes.sizeof(D), D.weight.offset, D.out.offset, D.tc_split.offset) == (size, o_w, o_out, o_r2)
 
 
 @pytest.mark.parametrize("case", list(CASE_KWARGS))

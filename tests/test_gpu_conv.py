@@ -187,3 +187,96 @@ def test_window_attention_block(dim, ws, shift, hw):
     att = E.window_attention(qkv, m.attn.bias_matrix().cuda().contiguous(), 8, ws, shift)
     out = E.conv_new(pack_linear(m.attn.proj, E.device, "proj"), [att], L.EPI_ADD, r1=xa)
     _close(_nchw(out), ref, rtol=5e-5)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# tcgen05 path (3xTF32 split accumulation): same contract as the SIMT kernel
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,k,stride,hw", [(192, 192, 5, 2, (32, 48)), (192, 320, 5, 2, (16, 24)),
+                                                   (96, 96, 3, 1, (16, 24)), (192, 96, 1, 1, (9, 7)),
+                                                   (288, 256, 3, 2, (8, 12)), (64, 32, 3, 1, (32, 48)),
+                                                   (224, 176, 3, 1, (5, 11)), (176, 128, 3, 1, (7, 9)),
+                                                   (320, 640, 5, 2, (8, 8)), (192, 576, 1, 1, (16, 16))])
+def test_tc_conv2d_matches_torch_and_simt(cin, cout, k, stride, hw):
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import pack_conv2d
+
+    E_tc, E_simt = _engine(2), _engine(1)
+    torch.manual_seed(cin + cout + k)
+    m = nn.Conv2d(cin, cout, k, stride, k // 2)
+    x = torch.randn(3, cin, *hw)
+    ref = m(x).detach()
+    pc = pack_conv2d(m, E_tc.device, "t").attach_tc(3)
+    assert pc.tc is not None
+    got = _nchw(E_tc.conv_new(pc, [_nhwc(x)]))
+    _close(got, ref)
+    simt = _nchw(E_simt.conv_new(pc, [_nhwc(x)]))
+    _close(got, simt)
+    _close(_nchw(E_tc.conv_new(pc, [_nhwc(x)], L.EPI_GELU)), F.gelu(ref))
+    # plain TF32 (1 product): ~1e-3 relative
+    pc.tc_split = 1
+    _close(_nchw(E_tc.conv_new(pc, [_nhwc(x)])), ref, rtol=2e-3)
+
+
+def test_tc_first_conv_gdn_deconv_shuffle_concat():
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import (new_act, pack_conv2d, pack_deconv_phases, pack_first_conv_im2col, pack_gdn)
+    from progressivecodec_b200.layers import GDN
+    from progressivecodec_b200.synthetic import synthetic_tensor
+
+    E = _engine(2)
+    torch.manual_seed(0)
+    # first conv through im2col (K = 80: partial last slab)
+    m = nn.Conv2d(3, 192, 5, 2, 2)
+    x = torch.rand(2, 3, 64, 128)
+    pc = pack_first_conv_im2col(m, E.device, 80, "c0").attach_tc()
+    _close(_nchw(E.conv_new(pc, [E.im2col_first(x.cuda(), 5, 2, 2, 80)])), m(x).detach())
+    # GDN / IGDN
+    for inverse in (False, True):
+        g = GDN(192, inverse=inverse)
+        with torch.no_grad():
+            g.beta.copy_(synthetic_tensor("g.beta", g.beta, 0))
+            g.gamma.copy_(synthetic_tensor("g.gamma", g.gamma, 0))
+        xx = torch.randn(2, 192, 12, 20)
+        beta, gamma = g.effective()
+        norm = F.conv2d(xx * xx, gamma.reshape(192, 192, 1, 1), beta)
+        ref = xx * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
+        _close(_nchw(E.gdn_new(pack_gdn(g, E.device, "g").attach_tc(), _nhwc(xx), inverse)), ref)
+    # transposed conv phases
+    md = nn.ConvTranspose2d(320, 192, 5, 2, 2, 1)
+    xd = torch.randn(2, 320, 4, 6)
+    ph = [p.attach_tc() for p in pack_deconv_phases(md, E.device, "d")]
+    _close(_nchw(E.deconv_new(ph, _nhwc(xd))), md(xd).detach())
+    # sub-pixel conv
+    ms = nn.Conv2d(192, 224 * 4, 3, 1, 1)
+    xs = torch.randn(2, 192, 4, 6)
+    _close(_nchw(E.conv_shuffle_new(pack_conv2d(ms, E.device, "s").attach_tc(), _nhwc(xs), L.EPI_GELU)),
+           F.gelu(F.pixel_shuffle(ms(xs), 2)).detach())
+    # virtual concat + LRP epilogue into a channel window
+    lm, yb, yp = torch.randn(2, 640, 8, 12), torch.randn(2, 320, 8, 12), torch.randn(2, 32, 8, 12)
+    mc = nn.Conv2d(320 + 96 + 32, 224, 3, 1, 1)
+    ref = mc(torch.cat([lm[:, 320:], yb[:, 64:160], yp], 1)).detach()
+    segs = [_nhwc(lm).slice(320, 320), _nhwc(yb).slice(64, 96), _nhwc(yp)]
+    _close(_nchw(E.conv_new(pack_conv2d(mc, E.device, "cat").attach_tc(), segs)), ref)
+    m2 = nn.Conv2d(64, 32, 3, 1, 1)
+    hh, r1, r2 = torch.randn(2, 64, 8, 12), torch.randn(2, 32, 8, 12), torch.randn(2, 32, 8, 12)
+    buf = new_act(2, 8, 12, 320, E.device)
+    buf.t.fill_(7.0)
+    out = buf.slice(96, 32)
+    E.conv(pack_conv2d(m2, E.device, "e").attach_tc(), [_nhwc(hh)], out, L.EPI_LRP, r1=_nhwc(r1), r2=_nhwc(r2))
+    _close(_nchw(out), r1 + 0.5 * torch.tanh(m2(hh).detach()) + r2)
+    assert (buf.t[..., :96] == 7.0).all() and (buf.t[..., 128:] == 7.0).all()
+
+
+def test_tc_conv_is_batch_invariant_and_deterministic():
+    from progressivecodec_b200.engine import pack_conv2d
+
+    E = _engine(2)
+    torch.manual_seed(5)
+    m = nn.Conv2d(352, 224, 3, 1, 1)
+    x = torch.randn(5, 352, 32, 48)
+    pc = pack_conv2d(m, E.device, "b").attach_tc()
+    full = _nchw(E.conv_new(pc, [_nhwc(x)]))
+    assert torch.equal(full, _nchw(E.conv_new(pc, [_nhwc(x)])))
+    for b in (0, 3, 4):
+        assert torch.equal(_nchw(E.conv_new(pc, [_nhwc(x[b:b + 1])]))[0], full[b])
