@@ -29,7 +29,8 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                  // fp32 elements per K slab = 128 bytes = one swizzle row
 constexpr int TC_A_BYTES = TC_BM * 128;    // one A tile (hi or lo)
-constexpr int TC_THREADS = 192;            // warps 0-3: A producers + epilogue, warp 4: TMA + TMEM alloc, warp 5: MMA
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_THREADS = 32 * (TC_PRODUCER_WARPS + 2);  // warps 0-7: A producers + epilogue, warp 8: TMA + TMEM alloc, warp 9: MMA
 constexpr int TC_SMEM_LIMIT = 220 * 1024;
 
 struct TcWeights {
@@ -182,16 +183,16 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < n_acc * bn) tmem_cols <<= 1;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == TC_PRODUCER_WARPS + 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_a(s), 128);
+      mbar_init(full_a(s), 32 * TC_PRODUCER_WARPS);
       mbar_init(full_b(s), 1);
       mbar_init(empty(s), 1);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == TC_PRODUCER_WARPS) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -201,16 +202,19 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   const int n0 = blockIdx.y * bn;
   const int n_steps = P.n_steps;
 
-  if (warp < 4) {
+  if (warp < TC_PRODUCER_WARPS) {
     // =============================== A producers ===============================
+    // 8 warps x 16 rows; a lane owns one 16-byte chunk (lane & 7) of 4 rows.  Loads run two K slabs ahead of the
+    // convert/store step so that ~2 slabs of global-load latency are in flight per thread.
+    constexpr int RPT = 4;       // rows per thread
     const int chunk = lane & 7;  // 16-byte chunk inside the 128-byte slab row
     const int sub = lane >> 3;
-    int64_t pix_base[8];
-    int ih0[8], iw0[8];
-    bool ok[8];
+    int64_t pix_base[RPT];
+    int ih0[RPT], iw0[RPT];
+    bool ok[RPT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = warp * 32 + i * 4 + sub;
+    for (int i = 0; i < RPT; ++i) {
+      const int row = warp * 16 + i * 4 + sub;
       const int64_t m = m0 + row;
       ok[i] = m < P.M;
       const int64_t mm = ok[i] ? m : 0;
@@ -224,14 +228,14 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     }
     const bool square = (d.flags & PCODEC_FLAG_SQUARE_INPUT) != 0;
     int seg = 0, tap = 0, kc = 0;  // kc: 32-channel slab inside the segment
-    float4 cur[8], nxt[8];
-    auto fetch = [&](float4 (&v)[8]) {
+    float4 cur[RPT], nx1[RPT], nx2[RPT];
+    auto fetch = [&](float4 (&v)[RPT]) {
       const pcodec_segment &sg = d.seg[seg];
       const int dy = d.dy[tap], dx = d.dx[tap];
       const int c = kc * TC_BK + chunk * 4;
       const bool c_ok = c < sg.channels;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < RPT; ++i) {
         const int iy = ih0[i] + dy, ix = iw0[i] + dx;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok[i] && c_ok && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w)
@@ -243,18 +247,19 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         if (++tap == d.n_taps) { tap = 0; ++seg; }
       }
     };
-    fetch(nxt);
+    fetch(nx1);
+    if (n_steps > 1) fetch(nx2);
     for (int s = 0; s < n_steps; ++s) {
       const int st = s % stages;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-      if (s + 1 < n_steps) fetch(nxt);
+      for (int i = 0; i < RPT; ++i) { cur[i] = nx1[i]; nx1[i] = nx2[i]; }
+      if (s + 2 < n_steps) fetch(nx2);
       mbar_wait(empty(st), ((s / stages) & 1) ^ 1);
       uint8_t *hi_base = smem_gen + (a_hi(st) - smem_base);
       uint8_t *lo_base = smem_gen + (a_lo(st) - smem_base);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = warp * 32 + i * 4 + sub;
+      for (int i = 0; i < RPT; ++i) {
+        const int row = warp * 16 + i * 4 + sub;
         const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
         float4 x = cur[i];
         if (square) { x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w; }
@@ -277,7 +282,9 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     // =============================== epilogue ===============================
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int row = warp * 32 + lane;  // TMEM lane == tile row
+    const int quarter = warp & 3;      // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    const int half = warp >> 2;        // warps w and w+4 share a quarter and interleave the 16-column groups
+    const int row = quarter * 32 + lane;  // TMEM lane == tile row
     const int64_t m = m0 + row;
     const bool row_ok = m < P.M;
     const int64_t mm = row_ok ? m : 0;
@@ -289,8 +296,8 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     const int64_t opix = (n * d.out_h + oh) * (int64_t)d.out_w + ow;
     const bool shuffle = (d.flags & PCODEC_FLAG_PIXEL_SHUFFLE2) != 0;
     const bool has_r2 = d.r2 != nullptr;
-    const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < bn; c0 += 16) {
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+    for (int c0 = half * 16; c0 < bn; c0 += 32) {
       float acc[16];
       tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective: executed by all lanes, stores are predicated
       for (int a = 1; a < n_acc; ++a) {
@@ -334,7 +341,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
       }
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == TC_PRODUCER_WARPS) {
     // =============================== TMA producer for B ===============================
     if (lane == 0) {
       int seg = 0, tap = 0, kc = 0, seg_cbase = 0;
@@ -384,7 +391,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     }
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_PRODUCER_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, tmem_cols);
   }
@@ -440,7 +447,7 @@ int pick_bn(int cout, int k_total) {
     const int bn = cout / tiles;
     if (bn % 16 != 0) continue;
     if (bn <= 256 && fallback == 0) fallback = bn;
-    if (bn <= cap) return bn;
+    if (bn <= cap) return (fallback != 0 && tiles > 2 * (cout / fallback)) ? fallback : bn;
   }
   return fallback;
 }

@@ -134,6 +134,8 @@ class ChannelProgresssiveWACNN(nn.Module):
         # execution knobs (not part of the reference API): tcgen05 path on/off, TF32 products per MAC in g_s
         self.tensor_cores = True
         self.synthesis_tf32_passes = 3
+        self.decode_groups = 0          # 0 = auto (B // 4 capped at 4): image groups decoded on separate CUDA streams
+        self._streams = None
 
     # ------------------------------------------------------------------------------------------------------
     # state handling
@@ -648,7 +650,12 @@ class ChannelProgresssiveWACNN(nn.Module):
 
     @torch.no_grad()
     def decompress(self, strings, shape, quality, mask_pol=None, cust_map=None):
-        """CHProg_cnn.py:849-999."""
+        """CHProg_cnn.py:849-999.
+
+        The decoder is a strictly serial chain per image (slice i's sigma needs the decoded slice i-1), and one
+        rANS stream is a serial state chain, so a batch is decoded as `decode_groups` image groups, each on its
+        own CUDA stream (one host thread per group): while one group's streams are being entropy-decoded by a
+        handful of warps, the tensor cores run another group's parameter networks."""
         if cust_map is not None:
             raise NotImplementedError("cust_map is outside the hot path (SURVEY.md §8f)")
         mask_pol = self.mask_policy if mask_pol is None else mask_pol
@@ -662,10 +669,56 @@ class ChannelProgresssiveWACNN(nn.Module):
             B = len(strings[1])
             z_data, z_off = _ans.pack_streams(list(strings[1]), dev)
             y_data, y_off = _ans.pack_streams([s for sl in strings[0] for s in sl], dev)
+        y_off_dev = y_off.to(dev)
+        z_off_dev = z_off.to(dev)
+        groups = self.decode_groups if self.decode_groups else max(1, min(4, B // 4))
+        groups = max(1, min(groups, B))
+        if groups == 1:
+            return {"x_hat": self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, 0, B, shape, quality,
+                                                    mask_pol)}
+        import threading
+
+        from .sharding import shard_bounds
+
+        cur = torch.cuda.current_stream(dev)
+        if self._streams is None or len(self._streams) < groups:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(groups)]
+        outs: List[Optional[Tensor]] = [None] * groups
+        errs: List[Optional[BaseException]] = [None] * groups
+
+        def work(g):
+            try:
+                lo, hi = shard_bounds(B, g, groups)
+                st = self._streams[g]
+                st.wait_stream(cur)
+                with torch.cuda.device(dev), torch.cuda.stream(st), torch.no_grad():
+                    outs[g] = self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, lo, hi, shape,
+                                                     quality, mask_pol)
+            except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
+                errs[g] = e
+
+        threads = [threading.Thread(target=work, args=(g,)) for g in range(groups)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+        for g in range(groups):
+            cur.wait_stream(self._streams[g])
+            outs[g].record_stream(cur)
+        return {"x_hat": torch.cat(outs, 0)}
+
+    def _decompress_group(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, quality, mask_pol):
+        """Decode images [lo, hi) of a batch whose streams are laid out slice-major: stream (s, b) = s*B_total + b."""
+        E: Engine = P["eng"]
+        dev = E.device
+        B = hi - lo
         hz, wz = int(shape[0]), int(shape[1])
         Cz = self.entropy_bottleneck._quantized_cdf.size(0)
         z_idx = E.bottleneck_indexes(B, hz * wz, Cz)
-        z_sym = _ans.decode_batch(z_data, z_off, z_idx, P["eb_tables"])
+        z_sym = _ans.decode_batch(z_data, z_off_dev[lo:hi + 1], z_idx, P["eb_tables"])
         z_hat = new_act(B, hz, wz, Cz, dev)
         E.bottleneck_dequantize(z_sym, P["medians"], z_hat)
         lm, ls = self._latents(P, z_hat, enhanced=not (quality == 0))
@@ -673,20 +726,19 @@ class ChannelProgresssiveWACNN(nn.Module):
         n = 32 * h * w
         table, bound = P["scale_table"], P["scale_bound"]
         tables = P["gc_tables"]
-        y_off_dev = y_off.to(dev)
 
         def decode_slice(s, scale, mask_mode, thr, mu, y_pre):
             ind = torch.empty((B, n), dtype=torch.int32, device=dev)
             E.slice_quantize(None, None, None, scale, mask_mode, thr, table, bound, None, ind, None, None, None)
-            sy = _ans.decode_batch(y_data, y_off_dev[s * B:(s + 1) * B + 1], ind, tables)
+            sy = _ans.decode_batch(y_data, y_off_dev[s * B_total + lo:s * B_total + hi + 1], ind, tables)
             E.slice_dequantize(sy, mu, y_pre)
 
         y_hat_base = self._base_slices(
             P, lm, ls, lambda i, mu, scale, y_pre: decode_slice(i, scale, L.MASK_ONES, None, mu, y_pre))
         if quality == 0:
-            return {"x_hat": self._g_s(P, y_hat_base, 0, clamp=True)}
+            return self._g_s(P, y_hat_base, 0, clamp=True)
         y_hat_q = self._prog_slices(
             P, lm, ls, y_hat_base, quality, mask_pol,
             lambda i, mu, scale, mask_mode, thr, y_pre: decode_slice(self.ns0 + i, scale, mask_mode, thr, mu, y_pre),
             "codec")
-        return {"x_hat": self._g_s(P, y_hat_q, 1, clamp=True)}
+        return self._g_s(P, y_hat_q, 1, clamp=True)

@@ -56,7 +56,7 @@ def test_compress_decompress_vs_golden(case):
         # (1) per-stage symbol / index agreement with the oracle (which reproduces the reference bit for bit)
         z_equal, first, frac = _first_divergence(orc, x, q, pol, dbg)
         assert z_equal, "z symbols differ"
-        assert frac <= 1e-4 or frac * dbg["symbols"].shape[1] * dbg["symbols"].shape[2] <= 1.0, (case, q, first, frac)
+        assert frac <= 1e-4 or frac * dbg["symbols"].shape[1] * dbg["symbols"].shape[2] <= 1.5, (case, q, first, frac)
         # (2) rate within 0.5 %
         b_gpu, b_ref = _total_bytes(out["strings"]), _total_bytes(ref_strings)
         assert abs(b_gpu - b_ref) <= 0.005 * b_ref + 8, (case, q, b_gpu, b_ref)
@@ -125,7 +125,7 @@ def test_symbol_disagreement_per_stage_mid_size():
     out = net.compress(x.cuda(), quality=2.5, debug=dbg)
     z_equal, first, frac = _first_divergence(orc, x, 2.5, None, dbg)
     assert z_equal
-    assert frac <= 1e-4 or frac * dbg["symbols"].shape[1] * dbg["symbols"].shape[2] <= 1.0, (first, frac)
+    assert frac <= 1e-4 or frac * dbg["symbols"].shape[1] * dbg["symbols"].shape[2] <= 1.5, (first, frac)  # <= 1 element
     t = orc.gc
     cd, cs, of = t.cdf.numpy(), t.cdf_length.numpy(), t.offset.numpy()
     sym, idx = dbg["symbols"].cpu().numpy(), dbg["indexes"].cpu().numpy()
