@@ -20,6 +20,8 @@
 // The K order (segment, tap, channel slab; hi*hi, lo*hi, hi*lo) is fixed: deterministic and batch invariant.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -183,9 +185,23 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < n_acc * bn) tmem_cols <<= 1;
 
+  __shared__ int s_dy[PCODEC_MAX_TAPS], s_dx[PCODEC_MAX_TAPS];
+  __shared__ const float *s_seg_ptr[PCODEC_MAX_SEGMENTS];
+  __shared__ int s_seg_ch[PCODEC_MAX_SEGMENTS], s_seg_ps[PCODEC_MAX_SEGMENTS];
+  if (threadIdx.x < PCODEC_MAX_TAPS) {
+    s_dy[threadIdx.x] = threadIdx.x < d.n_taps ? d.dy[threadIdx.x] : 0;
+    s_dx[threadIdx.x] = threadIdx.x < d.n_taps ? d.dx[threadIdx.x] : 0;
+  }
+  if (threadIdx.x < PCODEC_MAX_SEGMENTS) {
+    const bool in = (int)threadIdx.x < d.n_segments;
+    s_seg_ptr[threadIdx.x] = in ? d.seg[threadIdx.x].ptr : nullptr;
+    s_seg_ch[threadIdx.x] = in ? d.seg[threadIdx.x].channels : 0;
+    s_seg_ps[threadIdx.x] = in ? d.seg[threadIdx.x].pixel_stride : 0;
+  }
+
   if (warp == TC_PRODUCER_WARPS + 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_a(s), 32 * TC_PRODUCER_WARPS);
+      mbar_init(full_a(s), 128);  // one 4-warp producer group per slab
       mbar_init(full_b(s), 1);
       mbar_init(empty(s), 1);
     }
@@ -204,64 +220,86 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 
   if (warp < TC_PRODUCER_WARPS) {
     // =============================== A producers ===============================
-    // 8 warps x 16 rows; a lane owns one 16-byte chunk (lane & 7) of 4 rows.  Loads run two K slabs ahead of the
-    // convert/store step so that ~2 slabs of global-load latency are in flight per thread.
-    constexpr int RPT = 4;       // rows per thread
+    // Two groups of 4 warps alternate K slabs (group g builds slabs g, g+2, ...), so each group has two slab
+    // times to gather, split and store its 128x32 tile; inside a group a lane owns one 16-byte chunk (lane & 7)
+    // of 8 rows and keeps the loads of its next two slabs in flight (three rotating register buffers, loop
+    // unrolled by 3 so the rotation costs no moves).  Per-row state is a 32-bit pixel index; a tap only adds a
+    // uniform pixel offset, so changing tap costs one 64-bit multiply-add per row.
+    constexpr int RPT = 8;       // rows per thread
+    const int grp = warp >> 2, gw = warp & 3;
     const int chunk = lane & 7;  // 16-byte chunk inside the 128-byte slab row
     const int sub = lane >> 3;
-    int64_t pix_base[RPT];
-    int ih0[RPT], iw0[RPT];
-    bool ok[RPT];
+    int pix0[RPT];               // pixel index of (n, h*in_step, w*in_step) in the input image stack
+    int ih0[RPT], iw0[RPT];      // ih0 = INT_MIN/2 marks a row beyond M (never valid)
+    uint32_t soff[RPT];          // swizzled byte offset of (row, chunk) inside an A tile
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-      const int row = warp * 16 + i * 4 + sub;
+      const int row = gw * 32 + i * 4 + sub;
       const int64_t m = m0 + row;
-      ok[i] = m < P.M;
-      const int64_t mm = ok[i] ? m : 0;
+      const bool okr = m < P.M;
+      const int64_t mm = okr ? m : 0;
       const int w = (int)(mm % d.grid_w);
       const int64_t t = mm / d.grid_w;
       const int h = (int)(t % d.grid_h);
-      const int64_t n = t / d.grid_h;
-      pix_base[i] = n * d.in_h * (int64_t)d.in_w;
-      ih0[i] = h * d.in_step;
+      const int n = (int)(t / d.grid_h);
+      ih0[i] = okr ? h * d.in_step : -(1 << 28);
       iw0[i] = w * d.in_step;
+      pix0[i] = (n * d.in_h + h * d.in_step) * d.in_w + w * d.in_step;
+      soff[i] = row * 128 + ((chunk ^ (row & 7)) << 4);
     }
     const bool square = (d.flags & PCODEC_FLAG_SQUARE_INPUT) != 0;
+    const int in_h = d.in_h, in_w = d.in_w, n_taps = d.n_taps, n_segments = d.n_segments;
     int seg = 0, tap = 0, kc = 0;  // kc: 32-channel slab inside the segment
-    float4 cur[RPT], nx1[RPT], nx2[RPT];
-    auto fetch = [&](float4 (&v)[RPT]) {
-      const pcodec_segment &sg = d.seg[seg];
-      const int dy = d.dy[tap], dx = d.dx[tap];
-      const int c = kc * TC_BK + chunk * 4;
-      const bool c_ok = c < sg.channels;
+    const float *rowptr[RPT];
+    uint32_t rowmask = 0;          // bit i: row i reads real data for the current tap
+    int seg_slabs = 0, seg_channels = 0;
+    auto retarget = [&]() {        // (seg, tap) changed: recompute the per-row source pointers
+      const float *base = s_seg_ptr[seg] + chunk * 4;
+      const int ps = s_seg_ps[seg];
+      const int dy = s_dy[tap], dx = s_dx[tap];
+      const int tapoff = dy * in_w + dx;
+      seg_channels = s_seg_ch[seg];
+      seg_slabs = (seg_channels + TC_BK - 1) / TC_BK;
+      rowmask = 0;
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        const int iy = ih0[i] + dy, ix = iw0[i] + dx;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok[i] && c_ok && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w)
-          x = __ldg(reinterpret_cast<const float4 *>(sg.ptr + (pix_base[i] + (int64_t)iy * d.in_w + ix) * sg.pixel_stride + c));
-        v[i] = x;
-      }
-      if (++kc == (sg.channels + TC_BK - 1) / TC_BK) {
-        kc = 0;
-        if (++tap == d.n_taps) { tap = 0; ++seg; }
+        const bool v = (unsigned)(ih0[i] + dy) < (unsigned)in_h && (unsigned)(iw0[i] + dx) < (unsigned)in_w;
+        rowptr[i] = base + (int64_t)(v ? pix0[i] + tapoff : 0) * ps;
+        rowmask |= (v ? 1u : 0u) << i;
       }
     };
-    fetch(nx1);
-    if (n_steps > 1) fetch(nx2);
-    for (int s = 0; s < n_steps; ++s) {
-      const int st = s % stages;
+    auto advance2 = [&]() {        // step the (seg, tap, kc) iterator by two slabs
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) { cur[i] = nx1[i]; nx1[i] = nx2[i]; }
-      if (s + 2 < n_steps) fetch(nx2);
-      mbar_wait(empty(st), ((s / stages) & 1) ^ 1);
-      uint8_t *hi_base = smem_gen + (a_hi(st) - smem_base);
-      uint8_t *lo_base = smem_gen + (a_lo(st) - smem_base);
+      for (int r = 0; r < 2; ++r) {
+        if (++kc == seg_slabs) {
+          kc = 0;
+          if (++tap == n_taps) { tap = 0; ++seg; }
+          if (seg < n_segments) retarget();
+        }
+      }
+    };
+    auto fetch = [&](float4 (&v)[RPT]) {
+      const int c = kc * TC_BK + chunk * 4;
+      const bool c_ok = c < seg_channels;
+      const uint32_t mask = c_ok ? rowmask : 0u;
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        const int row = warp * 16 + i * 4 + sub;
-        const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
-        float4 x = cur[i];
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((mask >> i) & 1u) x = __ldg(reinterpret_cast<const float4 *>(rowptr[i] + kc * TC_BK));
+        v[i] = x;
+      }
+      advance2();
+    };
+    int st = grp % stages;                 // ring slot of this group's current slab
+    uint32_t ph = ((grp / stages) & 1) ^ 1; // parity to wait for on `empty`
+    uint8_t *a_tiles = smem_gen;           // generic pointer to stage 0
+    auto produce = [&](float4 (&v)[RPT]) {
+      mbar_wait(empty(st), ph);
+      uint8_t *hi_base = a_tiles + (size_t)st * stage_bytes;
+      uint8_t *lo_base = hi_base + TC_A_BYTES;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        float4 x = v[i];
         if (square) { x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w; }
         if (split) {
           float4 h, l;
@@ -269,14 +307,33 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-          *reinterpret_cast<float4 *>(hi_base + off) = h;
-          *reinterpret_cast<float4 *>(lo_base + off) = l;
+          *reinterpret_cast<float4 *>(hi_base + soff[i]) = h;
+          *reinterpret_cast<float4 *>(lo_base + soff[i]) = l;
         } else {
-          *reinterpret_cast<float4 *>(hi_base + off) = x;
+          *reinterpret_cast<float4 *>(hi_base + soff[i]) = x;
         }
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(full_a(st));
+      st += 2;                   // next slab of this group is two ring slots further
+      while (st >= stages) { st -= stages; ph ^= 1u; }
+    };
+    retarget();
+    if (grp == 1) {  // group 1 starts at slab 1
+      if (++kc == seg_slabs) { kc = 0; if (++tap == n_taps) { tap = 0; ++seg; } if (seg < n_segments) retarget(); }
+    }
+    float4 b0[RPT], b1[RPT], b2[RPT];
+    if (grp < n_steps) fetch(b0);
+    if (grp + 2 < n_steps) fetch(b1);
+    for (int s = grp; s < n_steps; s += 6) {
+      if (s + 4 < n_steps) fetch(b2);
+      produce(b0);
+      if (s + 2 >= n_steps) break;
+      if (s + 6 < n_steps) fetch(b0);
+      produce(b1);
+      if (s + 4 >= n_steps) break;
+      if (s + 8 < n_steps) fetch(b1);
+      produce(b2);
     }
 
     // =============================== epilogue ===============================
@@ -345,9 +402,11 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     // =============================== TMA producer for B ===============================
     if (lane == 0) {
       int seg = 0, tap = 0, kc = 0, seg_cbase = 0;
-      for (int s = 0; s < n_steps; ++s) {
-        const int st = s % stages;
-        mbar_wait(empty(st), ((s / stages) & 1) ^ 1);
+      int st = 0;
+      uint32_t ph = 1;
+      for (int s = 0; s < n_steps; ++s, ++st) {
+        if (st == stages) { st = 0; ph ^= 1u; }
+        mbar_wait(empty(st), ph);
         const int k = tap * d.cin_total + seg_cbase + kc * TC_BK;
         mbar_expect_tx(full_b(st), (uint32_t)((split ? 2 : 1) * b_bytes));
         tma_load_2d(b_hi(st), &map_hi, full_b(st), k, n0);
@@ -364,15 +423,16 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     if (lane == 0) {
       // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int s = 0; s < n_steps; ++s) {
-        const int st = s % stages;
-        const uint32_t ph = (s / stages) & 1;
+      int st = 0, hi_idx = 0;
+      uint32_t ph = 0;
+      for (int s = 0; s < n_steps; ++s, ++st, ++hi_idx) {
+        if (st == stages) { st = 0; ph ^= 1u; }
+        if (hi_idx == P.n_hi_acc) hi_idx = 0;
         mbar_wait(full_a(st), ph);
         mbar_wait(full_b(st), ph);
         tc_fence_after();
         const uint64_t da_hi = umma_desc_sw128(a_hi(st)), db_hi = umma_desc_sw128(b_hi(st));
         const uint64_t da_lo = umma_desc_sw128(a_lo(st)), db_lo = umma_desc_sw128(b_lo(st));
-        const int hi_idx = s % P.n_hi_acc;
         const uint32_t acc_hi = tmem_acc + (uint32_t)(hi_idx * bn);
         const uint32_t acc_lo = tmem_acc + (uint32_t)(P.n_hi_acc * bn);
         const bool first_hi = s < P.n_hi_acc;  // first slab that touches this hi accumulator
@@ -440,7 +500,8 @@ __global__ void split_weights_kernel(const float *__restrict__ w_tap_major, int 
 // result at fp32-class accuracy (measured: rms 1e-5 -> 3e-6 at K = 4800).
 int pick_bn(int cout, int k_total) {
   if (cout % 16 != 0) return 0;
-  const int cap = k_total >= 1024 ? 128 : 256;
+  int cap = k_total >= 1024 ? 128 : 256;
+  if (const char *e = getenv("PCODEC_TC_BNCAP")) cap = atoi(e);  // experiment knob
   int fallback = 0;
   for (int tiles = 1; tiles <= 16; ++tiles) {
     if (cout % tiles) continue;
@@ -531,6 +592,7 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   const int stage_bytes = (P.split == 3 ? 2 : 1) * (TC_A_BYTES + h->bn * 128);
   int stages = (TC_SMEM_LIMIT - 2048) / stage_bytes;
   if (stages > 6) stages = 6;
+  if (const char *e = getenv("PCODEC_TC_STAGES")) stages = std::min(stages, atoi(e));  // experiment knob
   if (stages > n_steps) stages = n_steps;
   if (stages < 1) return PCODEC_ERR_UNSUPPORTED;
   P.stages = stages;
