@@ -6,6 +6,7 @@ one-off weight repacking at prepare() time.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -20,24 +21,47 @@ def _stream():
 
 
 class Act:
-    """View of `C` channels starting at `c0` of an NHWC fp32 tensor [B, H, W, Ctot]."""
+    """View of `C` channels starting at `c0` of an NHWC fp32 buffer [B, H, W, ps].
 
-    __slots__ = ("t", "B", "H", "W", "C", "c0", "ps")
+    Backed either by a torch tensor (`t`) or by a raw range of an `Arena`; kernels only need `ptr`/`ps`, so
+    arena-backed views never construct a torch tensor on the hot path (`t` is materialised lazily)."""
 
-    def __init__(self, t: Tensor, c0: int = 0, channels: Optional[int] = None):
-        assert t.dim() == 4 and t.dtype == torch.float32 and t.is_contiguous()
-        self.t = t
-        self.B, self.H, self.W, self.ps = t.shape
+    __slots__ = ("_t", "base", "B", "H", "W", "C", "c0", "ps", "_owner")
+
+    def __init__(self, t: Optional[Tensor] = None, c0: int = 0, channels: Optional[int] = None, *, base: int = 0,
+                 shape: Optional[Tuple[int, int, int, int]] = None, owner=None):
+        if t is not None:
+            assert t.dim() == 4 and t.dtype == torch.float32 and t.is_contiguous()
+            self._t = t
+            self.base = t.data_ptr()
+            self.B, self.H, self.W, self.ps = t.shape
+            self._owner = None
+        else:
+            self._t = None
+            self.base = base
+            self.B, self.H, self.W, self.ps = shape
+            self._owner = owner
         self.c0 = c0
         self.C = self.ps - c0 if channels is None else channels
         assert 0 <= c0 and c0 + self.C <= self.ps
 
     @property
     def ptr(self) -> int:
-        return self.t.data_ptr() + 4 * self.c0
+        return self.base + 4 * self.c0
+
+    @property
+    def t(self) -> Tensor:
+        if self._t is None:
+            self._t = self._owner.view(self.base, (self.B, self.H, self.W, self.ps))
+        return self._t
 
     def slice(self, c0: int, channels: int) -> "Act":
-        return Act(self.t, self.c0 + c0, channels)
+        a = Act.__new__(Act)
+        a._t, a.base, a._owner = self._t, self.base, self._owner
+        a.B, a.H, a.W, a.ps = self.B, self.H, self.W, self.ps
+        a.c0, a.C = self.c0 + c0, channels
+        assert a.c0 + channels <= self.ps
+        return a
 
     def dense(self) -> Tensor:
         return self.t[..., self.c0:self.c0 + self.C]
@@ -45,6 +69,56 @@ class Act:
 
 def new_act(B: int, H: int, W: int, channels: int, device) -> Act:
     return Act(torch.empty((B, H, W, channels), dtype=torch.float32, device=device))
+
+
+class Arena:
+    """Bump allocator over one device buffer.  An inference call performs the same sequence of allocations
+    every time it sees the same shapes, so resetting the arena at the start of a call makes every activation
+    land at the same address as last time — which lets the engine reuse fully built kernel descriptors."""
+
+    def __init__(self, device, nbytes: int = 64 << 20):
+        self.device = device
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.off = 0
+        self.generation = 0
+        self.retired: List[Tensor] = []
+
+    def reset(self) -> None:
+        self.off = 0
+        self.retired.clear()  # buffers replaced during the previous call are no longer referenced by kernels in flight
+                              # on this stream only after the next sync; they stay alive until the following reset
+
+    def alloc(self, nbytes: int) -> int:
+        nbytes = (nbytes + 255) & ~255
+        if self.off + nbytes > self.buf.numel():
+            # grow: keep the old buffer alive (kernels in flight / live views), start a fresh, larger one
+            self.retired.append(self.buf)
+            self.buf = torch.empty(max(2 * self.buf.numel(), self.off + nbytes + (64 << 20)), dtype=torch.uint8,
+                                   device=self.device)
+            self.off = 0
+            self.generation += 1
+        p = self.buf.data_ptr() + self.off
+        self.off += nbytes
+        return p
+
+    def mark(self):
+        return (self.generation, self.off)
+
+    def release(self, mark) -> None:
+        """Give back everything allocated since `mark` (stack discipline).  Safe because every kernel that touches
+        the released range was enqueued on this context's stream before any later kernel that reuses it."""
+        if mark[0] == self.generation:
+            self.off = mark[1]
+
+    def view(self, ptr: int, shape) -> Tensor:
+        for b in [self.buf] + self.retired:
+            o = ptr - b.data_ptr()
+            if 0 <= o < b.numel():
+                n = 1
+                for d in shape:
+                    n *= d
+                return b[o:o + 4 * n].view(torch.float32).view(*shape)
+        raise RuntimeError("pointer does not belong to this arena")
 
 
 class PackedConv:
@@ -139,6 +213,21 @@ def pack_gdn(g, device, name="") -> PackedConv:
                       beta.to(device=device, dtype=torch.float32), [(0, 0)], name=name)
 
 
+class _ArenaScope:
+    __slots__ = ("arena", "m")
+
+    def __init__(self, arena: Arena):
+        self.arena = arena
+
+    def __enter__(self):
+        self.m = self.arena.mark()
+        return self
+
+    def __exit__(self, *exc):
+        self.arena.release(self.m)
+        return False
+
+
 class Engine:
     """Stateless helpers that launch kernels on the current stream."""
 
@@ -146,10 +235,64 @@ class Engine:
         self.device = device
         self.lib = L.lib()
         self.conv_impl = conv_impl
+        self._tls = threading.local()
+        self._slots = {}
+        self._slots_lock = threading.Lock()
+
+    # -- per-slot call state: arena, stream handle, cached descriptors -----------------------------------
+    class _Ctx:
+        __slots__ = ("arena", "descs", "stream")
+
+    def begin(self, slot: int = 0) -> None:
+        """Start of an inference call: bind this thread to context `slot` (slot 0 = caller's thread, slot g+1 =
+        decode group g), rewind its arena and latch the current CUDA stream."""
+        with self._slots_lock:
+            ctx = self._slots.get(slot)
+            if ctx is None:
+                ctx = Engine._Ctx()
+                ctx.arena = Arena(self.device)
+                ctx.descs = {}
+                self._slots[slot] = ctx
+        ctx.arena.reset()
+        ctx.stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._tls.ctx = ctx
+
+    def _state(self):
+        ctx = getattr(self._tls, "ctx", None)
+        if ctx is None:
+            self.begin(0)
+            ctx = self._tls.ctx
+        return ctx
+
+    def stream(self) -> int:
+        return self._state().stream
+
+    def scope(self):
+        """`with E.scope():` — activations allocated inside are temporaries, released on exit."""
+        return _ArenaScope(self._state().arena)
+
+    def act(self, B: int, H: int, W: int, channels: int) -> Act:
+        """Arena-backed NHWC activation (valid until the next begin() on this thread)."""
+        ar = self._state().arena
+        return Act(base=ar.alloc(4 * B * H * W * channels), shape=(B, H, W, channels), owner=ar)
 
     # -- generic tap conv --------------------------------------------------------------------------------
     def conv(self, pc: PackedConv, segs: Sequence[Act], out: Act, epi: int = L.EPI_LINEAR, r1: Optional[Act] = None,
              r2: Optional[Act] = None, flags: int = 0) -> Act:
+        tls = self._state()
+        key = (id(pc), pc.w.data_ptr(), pc.tc, pc.tc_split, out.ptr, out.ps, epi, flags, r1.ptr if r1 is not None else 0,
+               r2.ptr if r2 is not None else 0, segs[0].B, segs[0].H, segs[0].W) + tuple((s.ptr, s.C, s.ps) for s in segs)
+        d = tls.descs.get(key)
+        if d is None:
+            d = self._build_desc(pc, segs, out, epi, r1, r2, flags)
+            if len(tls.descs) > 20000:
+                tls.descs.clear()
+            tls.descs[key] = d
+        L.check(self.lib.pcodec_conv_taps(d, self.conv_impl, tls.stream), pc.name)
+        return out
+
+    def _build_desc(self, pc: PackedConv, segs: Sequence[Act], out: Act, epi: int, r1: Optional[Act],
+                    r2: Optional[Act], flags: int):
         a0 = segs[0]
         d = L.ConvDesc()
         cin = 0
@@ -181,8 +324,7 @@ class Engine:
         d.out_step, d.out_off_y, d.out_off_x = pc.out_step, pc.off[0], pc.off[1]
         if shuffle:
             assert (out.H, out.W, out.C) == (2 * oh, 2 * ow, pc.cout // 4), (pc.name, out.H, out.W, out.C)
-            d.out_h, d.out_w = 2 * oh, 2 * ow   # kernel indexes the shuffled tensor with these
-            # for the shuffled store the kernel computes (2*oh+si, 2*ow+sj) inside an [out_h, out_w] image
+            d.out_h, d.out_w = 2 * oh, 2 * ow   # the kernel indexes the shuffled tensor with these
         else:
             assert (out.H, out.W, out.C) == (oh, ow, pc.cout), (pc.name, (out.H, out.W, out.C), (oh, ow, pc.cout))
             d.out_h, d.out_w = oh, ow
@@ -195,58 +337,57 @@ class Engine:
         if r2 is not None:
             d.r2, d.r2_pixel_stride = r2.ptr, r2.ps
         d.tc_weights, d.tc_split = pc.tc, pc.tc_split
-        L.check(self.lib.pcodec_conv_taps(C.byref(d), self.conv_impl, _stream()), f"conv_taps[{pc.name}]")
-        return out
+        return d
 
     def conv_new(self, pc: PackedConv, segs: Sequence[Act], epi: int = L.EPI_LINEAR, r1=None, r2=None) -> Act:
         a0 = segs[0]
-        out = new_act(a0.B, a0.H // pc.in_step, a0.W // pc.in_step, pc.cout, self.device)
+        out = self.act(a0.B, a0.H // pc.in_step, a0.W // pc.in_step, pc.cout)
         return self.conv(pc, segs, out, epi, r1, r2)
 
     def conv_shuffle_new(self, pc: PackedConv, x: Act, epi: int) -> Act:
-        out = new_act(x.B, 2 * x.H, 2 * x.W, pc.cout // 4, self.device)
+        out = self.act(x.B, 2 * x.H, 2 * x.W, pc.cout // 4)
         return self.conv(pc, [x], out, epi, flags=L.FLAG_PIXEL_SHUFFLE2)
 
     def deconv_new(self, phases: List[PackedConv], x: Act, epi: int = L.EPI_LINEAR, out: Optional[Act] = None) -> Act:
         if out is None:
-            out = new_act(x.B, 2 * x.H, 2 * x.W, phases[0].cout, self.device)
+            out = self.act(x.B, 2 * x.H, 2 * x.W, phases[0].cout)
         for ph in phases:
             self.conv(ph, [x], out, epi)
         return out
 
     def gdn_new(self, pc: PackedConv, x: Act, inverse: bool) -> Act:
-        out = new_act(x.B, x.H, x.W, x.C, self.device)
+        out = self.act(x.B, x.H, x.W, x.C)
         return self.conv(pc, [x], out, L.EPI_IGDN if inverse else L.EPI_GDN, r1=x, flags=L.FLAG_SQUARE_INPUT)
 
     # -- attention -----------------------------------------------------------------------------------------
     def window_attention(self, qkv: Act, rel_bias: Tensor, heads: int, ws: int, shift: int) -> Act:
         Cn = qkv.C // 3
-        out = new_act(qkv.B, qkv.H, qkv.W, Cn, self.device)
+        out = self.act(qkv.B, qkv.H, qkv.W, Cn)
         L.check(self.lib.pcodec_window_attention(qkv.ptr, qkv.ps, out.ptr, out.ps, rel_bias.data_ptr(), qkv.B, qkv.H,
-                                                 qkv.W, Cn, heads, ws, shift, _stream()), "window_attention")
+                                                 qkv.W, Cn, heads, ws, shift, self.stream()), "window_attention")
         return out
 
     # -- layout ----------------------------------------------------------------------------------------------
     def im2col_first(self, x_nchw: Tensor, k: int, stride: int, pad: int, k_pad: int) -> Act:
         B, Cn, H, W = x_nchw.shape
         oh, ow = H // stride, W // stride
-        out = new_act(B, oh, ow, k_pad, self.device)
+        out = self.act(B, oh, ow, k_pad)
         L.check(self.lib.pcodec_im2col_nchw(x_nchw.data_ptr(), out.ptr, B, Cn, H, W, k, stride, pad, oh, ow, k_pad,
-                                            _stream()), "im2col_nchw")
+                                            self.stream()), "im2col_nchw")
         return out
 
     def to_nchw(self, a: Act) -> Tensor:
         out = torch.empty((a.B, a.C, a.H, a.W), dtype=torch.float32, device=self.device)
-        L.check(self.lib.pcodec_nhwc_to_nchw(a.ptr, a.ps, out.data_ptr(), a.B, a.C, a.H * a.W, _stream()),
+        L.check(self.lib.pcodec_nhwc_to_nchw(a.ptr, a.ps, out.data_ptr(), a.B, a.C, a.H * a.W, self.stream()),
                 "nhwc_to_nchw")
         return out
 
     def from_nchw(self, t: Tensor, c_pad: Optional[int] = None) -> Act:
         B, Cn, H, W = t.shape
         c_pad = c_pad or Cn
-        out = new_act(B, H, W, c_pad, self.device)
+        out = self.act(B, H, W, c_pad)
         t = t.contiguous().float()
-        L.check(self.lib.pcodec_nchw_to_nhwc(t.data_ptr(), out.ptr, B, Cn, H * W, c_pad, c_pad, _stream()),
+        L.check(self.lib.pcodec_nchw_to_nhwc(t.data_ptr(), out.ptr, B, Cn, H * W, c_pad, c_pad, self.stream()),
                 "nchw_to_nhwc")
         return out
 
@@ -255,7 +396,7 @@ class Engine:
         thr = torch.empty((scale.B,), dtype=torch.float32, device=self.device)
         L.check(self.lib.pcodec_quantile_threshold(scale.ptr, scale.B, scale.H * scale.W, scale.C, scale.ps,
                                                    float(torch.tensor(q, dtype=torch.float32).item()), thr.data_ptr(),
-                                                   None, _stream()), "quantile_threshold")
+                                                   None, self.stream()), "quantile_threshold")
         return thr
 
     def slice_quantize(self, y: Optional[Act], y_sub: Optional[Act], mu: Optional[Act], scale: Act, mask_mode: int,
@@ -268,32 +409,32 @@ class Engine:
         L.check(self.lib.pcodec_slice_quantize(ap(y), aps(y), ap(y_sub), aps(y_sub), ap(mu), aps(mu), scale.ptr,
                                                scale.ps, scale.B, scale.H * scale.W, scale.C, mask_mode, p(thr),
                                                table.data_ptr(), table.numel(), bound, p(symbols), p(indexes),
-                                               p(mask_out), p(lik), ap(y_hat), aps(y_hat), _stream()), "slice_quantize")
+                                               p(mask_out), p(lik), ap(y_hat), aps(y_hat), self.stream()), "slice_quantize")
 
     def slice_dequantize(self, symbols: Tensor, mu: Act, y_hat: Act) -> None:
         L.check(self.lib.pcodec_slice_dequantize(symbols.data_ptr(), mu.ptr, mu.ps, mu.B, mu.H * mu.W, mu.C, y_hat.ptr,
-                                                 y_hat.ps, _stream()), "slice_dequantize")
+                                                 y_hat.ps, self.stream()), "slice_dequantize")
 
     def bottleneck_quantize(self, z: Act, medians: Tensor, symbols: Optional[Tensor], indexes: Optional[Tensor],
                             z_hat: Optional[Act]) -> None:
         p = lambda t: t.data_ptr() if t is not None else None
         L.check(self.lib.pcodec_bottleneck_quantize(z.ptr, z.ps, medians.data_ptr(), z.B, z.H * z.W, z.C, p(symbols),
                                                     p(indexes), z_hat.ptr if z_hat else None,
-                                                    z_hat.ps if z_hat else 0, _stream()), "bottleneck_quantize")
+                                                    z_hat.ps if z_hat else 0, self.stream()), "bottleneck_quantize")
 
     def bottleneck_dequantize(self, symbols: Tensor, medians: Tensor, z_hat: Act) -> None:
         L.check(self.lib.pcodec_bottleneck_dequantize(symbols.data_ptr(), medians.data_ptr(), z_hat.B,
-                                                      z_hat.H * z_hat.W, z_hat.C, z_hat.ptr, z_hat.ps, _stream()),
+                                                      z_hat.H * z_hat.W, z_hat.C, z_hat.ptr, z_hat.ps, self.stream()),
                 "bottleneck_dequantize")
 
     def bottleneck_indexes(self, B: int, hw: int, channels: int) -> Tensor:
         idx = torch.empty((B, channels * hw), dtype=torch.int32, device=self.device)
-        L.check(self.lib.pcodec_bottleneck_indexes(B, hw, channels, idx.data_ptr(), _stream()), "bottleneck_indexes")
+        L.check(self.lib.pcodec_bottleneck_indexes(B, hw, channels, idx.data_ptr(), self.stream()), "bottleneck_indexes")
         return idx
 
     def bottleneck_likelihood(self, z_hat: Act, params: Tensor) -> Tensor:
         lik = torch.empty((z_hat.B, z_hat.C, z_hat.H, z_hat.W), dtype=torch.float32, device=self.device)
         L.check(self.lib.pcodec_bottleneck_likelihood(z_hat.ptr, z_hat.ps, params.data_ptr(), z_hat.B,
-                                                      z_hat.H * z_hat.W, z_hat.C, lik.data_ptr(), _stream()),
+                                                      z_hat.H * z_hat.W, z_hat.C, lik.data_ptr(), self.stream()),
                 "bottleneck_likelihood")
         return lik

@@ -274,41 +274,49 @@ class ChannelProgresssiveWACNN(nn.Module):
     @staticmethod
     def _ru(E: Engine, pk, x: Act, out: Optional[Act] = None) -> Act:
         """ResidualUnit (layers.py:39-59): 1x1 -> GELU -> 3x3 -> GELU -> 1x1 -> (+x) -> GELU."""
-        h = E.conv_new(pk[0], [x], L.EPI_GELU)
-        h = E.conv_new(pk[1], [h], L.EPI_GELU)
-        out = out or new_act(x.B, x.H, x.W, x.C, E.device)
-        return E.conv(pk[2], [h], out, L.EPI_ADD_GELU, r1=x)
+        out = out or E.act(x.B, x.H, x.W, x.C)
+        with E.scope():
+            h = E.conv_new(pk[0], [x], L.EPI_GELU)
+            h = E.conv_new(pk[1], [h], L.EPI_GELU)
+            E.conv(pk[2], [h], out, L.EPI_ADD_GELU, r1=x)
+        return out
 
     def _win(self, E: Engine, pk, x: Act, out: Optional[Act] = None) -> Act:
         """Win_noShift_Attention (layers.py:69-75)."""
-        a = x
-        for r in pk["a"]:
-            a = self._ru(E, r, a)
-        qkv = E.conv_new(pk["qkv"], [x])
-        att = E.window_attention(qkv, pk["rel"], pk["heads"], pk["ws"], pk["shift"])
-        b = E.conv_new(pk["proj"], [att], L.EPI_ADD, r1=x)
-        for r in pk["b"]:
-            b = self._ru(E, r, b)
-        out = out or new_act(x.B, x.H, x.W, x.C, E.device)
-        return E.conv(pk["out"], [b], out, L.EPI_GATE, r1=x, r2=a)
+        out = out or E.act(x.B, x.H, x.W, x.C)
+        with E.scope():
+            a = x
+            for r in pk["a"]:
+                a = self._ru(E, r, a)
+            b = E.act(x.B, x.H, x.W, x.C)
+            with E.scope():
+                qkv = E.conv_new(pk["qkv"], [x])
+                att = E.window_attention(qkv, pk["rel"], pk["heads"], pk["ws"], pk["shift"])
+                E.conv(pk["proj"], [att], b, L.EPI_ADD, r1=x)
+            for r in pk["b"]:
+                b = self._ru(E, r, b)
+            E.conv(pk["out"], [b], out, L.EPI_GATE, r1=x, r2=a)
+        return out
 
     def _g_a_one(self, E: Engine, pk, x: Tensor, out: Act) -> Act:
         """CHProg_cnn.py:131-144."""
-        h = E.im2col_first(x, 5, 2, 2, 80)
-        h = E.conv_new(pk["c0"], [h])
-        h = E.gdn_new(pk["g1"], h, False)
-        h = E.conv_new(pk["c2"], [h])
-        h = E.gdn_new(pk["g3"], h, False)
-        h = self._win(E, pk["w4"], h)
-        h = E.conv_new(pk["c5"], [h])
-        h = E.gdn_new(pk["g6"], h, False)
-        h = E.conv_new(pk["c7"], [h])
-        return self._win(E, pk["w8"], h, out)
+        with E.scope():
+            h = E.im2col_first(x, 5, 2, 2, 80)
+            h = E.conv_new(pk["c0"], [h])
+            h = E.gdn_new(pk["g1"], h, False)
+            h = E.conv_new(pk["c2"], [h])
+            h = E.gdn_new(pk["g3"], h, False)
+            h = self._win(E, pk["w4"], h)
+            h = E.conv_new(pk["c5"], [h])
+            h = E.gdn_new(pk["g6"], h, False)
+            h = E.conv_new(pk["c7"], [h])
+            self._win(E, pk["w8"], h, out)
+        return out
 
     def _g_a(self, P, x: Tensor) -> Act:
         E = P["eng"]
         B, _, H, W = x.shape
-        y = new_act(B, H // 16, W // 16, self.M, E.device)
+        y = E.act(B, H // 16, W // 16, self.M)
         if self.multiple_encoder:
             d0 = self.dimensions_M[0]
             self._g_a_one(E, P["g_a"][0], x, y.slice(0, d0))
@@ -321,31 +329,37 @@ class ChannelProgresssiveWACNN(nn.Module):
         """CHProg_cnn.py:148-161 (+ clamp_(0,1) of :909/:988 fused into the last deconv)."""
         E = P["eng"]
         pk = P["g_s"][which if self.multiple_decoder else 0]
-        h = self._win(E, pk["w0"], y_hat)
-        h = E.deconv_new(pk["d1"], h)
-        h = E.gdn_new(pk["g2"], h, True)
-        h = E.deconv_new(pk["d3"], h)
-        h = E.gdn_new(pk["g4"], h, True)
-        h = self._win(E, pk["w5"], h)
-        h = E.deconv_new(pk["d6"], h)
-        h = E.gdn_new(pk["g7"], h, True)
-        h = E.deconv_new(pk["d8"], h, L.EPI_CLAMP01 if clamp else L.EPI_LINEAR)
-        return E.to_nchw(h)
+        with E.scope():
+            h = self._win(E, pk["w0"], y_hat)
+            h = E.deconv_new(pk["d1"], h)
+            h = E.gdn_new(pk["g2"], h, True)
+            h = E.deconv_new(pk["d3"], h)
+            h = E.gdn_new(pk["g4"], h, True)
+            h = self._win(E, pk["w5"], h)
+            h = E.deconv_new(pk["d6"], h)
+            h = E.gdn_new(pk["g7"], h, True)
+            h = E.deconv_new(pk["d8"], h, L.EPI_CLAMP01 if clamp else L.EPI_LINEAR)
+            return E.to_nchw(h)
 
     def _h_a(self, P, y: Act) -> Act:
         E = P["eng"]
-        h = y
-        for j, pc in enumerate(P["h_a"]):
-            h = E.conv_new(pc, [h], L.EPI_GELU if j < 4 else L.EPI_LINEAR)
-        return h
+        out = E.act(y.B, y.H // 4, y.W // 4, P["h_a"][4].cout)
+        with E.scope():
+            h = y
+            for j, pc in enumerate(P["h_a"][:4]):
+                h = E.conv_new(pc, [h], L.EPI_GELU)
+            E.conv(P["h_a"][4], [h], out)
+        return out
 
     @staticmethod
     def _h_s(E: Engine, pk, z_hat: Act, out: Act) -> Act:
-        h = E.conv_new(pk[0], [z_hat], L.EPI_GELU)
-        h = E.conv_shuffle_new(pk[1], h, L.EPI_GELU)
-        h = E.conv_new(pk[2], [h], L.EPI_GELU)
-        h = E.conv_shuffle_new(pk[3], h, L.EPI_GELU)
-        return E.conv(pk[4], [h], out)
+        with E.scope():
+            h = E.conv_new(pk[0], [z_hat], L.EPI_GELU)
+            h = E.conv_shuffle_new(pk[1], h, L.EPI_GELU)
+            h = E.conv_new(pk[2], [h], L.EPI_GELU)
+            h = E.conv_shuffle_new(pk[3], h, L.EPI_GELU)
+            E.conv(pk[4], [h], out)
+        return out
 
     def _latents(self, P, z_hat: Act, enhanced: bool):
         """Which hyper-synthesis nets run: CHProg_cnn.py:404-417 / 705-715 / 856-867."""
@@ -353,12 +367,12 @@ class ChannelProgresssiveWACNN(nn.Module):
         B, h, w = z_hat.B, z_hat.H * 4, z_hat.W * 4
         d0 = self.dimensions_M[0]
         if not self.multiple_hyperprior:
-            lm, ls = new_act(B, h, w, self.M, E.device), new_act(B, h, w, self.M, E.device)
+            lm, ls = E.act(B, h, w, self.M), E.act(B, h, w, self.M)
             self._h_s(E, P["h_mean_s"][0], z_hat, lm)
             self._h_s(E, P["h_scale_s"][0], z_hat, ls)
             return lm, ls
         ctot = 2 * d0 if enhanced else d0
-        lm, ls = new_act(B, h, w, ctot, E.device), new_act(B, h, w, ctot, E.device)
+        lm, ls = E.act(B, h, w, ctot), E.act(B, h, w, ctot)
         self._h_s(E, P["h_mean_s"][0], z_hat, lm.slice(0, d0))
         self._h_s(E, P["h_scale_s"][0], z_hat, ls.slice(0, d0))
         if enhanced:
@@ -368,10 +382,12 @@ class ChannelProgresssiveWACNN(nn.Module):
 
     @staticmethod
     def _stack(E: Engine, pk, segs: Sequence[Act], out: Act, epi=L.EPI_LINEAR, r1=None, r2=None) -> Act:
-        h = E.conv_new(pk[0], segs, L.EPI_GELU)
-        for j in (1, 2, 3):
-            h = E.conv_new(pk[j], [h], L.EPI_GELU)
-        return E.conv(pk[4], [h], out, epi, r1, r2)
+        with E.scope():
+            h = E.conv_new(pk[0], segs, L.EPI_GELU)
+            for j in (1, 2, 3):
+                h = E.conv_new(pk[j], [h], L.EPI_GELU)
+            E.conv(pk[4], [h], out, epi, r1, r2)
+        return out
 
     @staticmethod
     def _merge_segments(E: Engine, acts: Sequence[Act]) -> List[Act]:
@@ -395,15 +411,15 @@ class ChannelProgresssiveWACNN(nn.Module):
         E = P["eng"]
         d0 = self.dimensions_M[0]
         B, h, w = lm.B, lm.H, lm.W
-        y_hat_base = new_act(B, h, w, d0, E.device)
+        y_hat_base = E.act(B, h, w, d0)
         lm0, ls0 = lm.slice(0, d0), ls.slice(0, d0)
         for i in range(self.ns0):
             k = min(self.max_support_slices, i)
             sup = [y_hat_base.slice(0, 32 * k)] if k > 0 else []
-            mu, scale = new_act(B, h, w, 32, E.device), new_act(B, h, w, 32, E.device)
+            mu, scale = E.act(B, h, w, 32), E.act(B, h, w, 32)
             self._stack(E, P["cc_mean_transforms"][i], [lm0] + sup, mu)
             self._stack(E, P["cc_scale_transforms"][i], [ls0] + sup, scale)
-            y_pre = new_act(B, h, w, 32, E.device)
+            y_pre = E.act(B, h, w, 32)
             code(i, mu, scale, y_pre)
             self._stack(E, P["lrp_transforms"][i], [lm0] + sup + [y_pre], y_hat_base.slice(32 * i, 32), L.EPI_LRP,
                         r1=y_pre)
@@ -418,14 +434,14 @@ class ChannelProgresssiveWACNN(nn.Module):
         d0 = self.dimensions_M[0]
         B, h, w = lm.B, lm.H, lm.W
         n_prog = self.ns1 - self.ns0
-        y_hat_q = new_act(B, h, w, 32 * n_prog, E.device)
+        y_hat_q = E.act(B, h, w, 32 * n_prog)
         lm1, ls1 = lm.slice(d0, lm.C - d0), ls.slice(d0, ls.C - d0)
         state = state if state is not None else {}
         mu_total: List[Act] = state.setdefault("mu_total", [])
         std_total: List[Act] = state.setdefault("std_total", [])
         if self.all_scalable:  # per-pass pools so that consecutive list entries are adjacent channel ranges
-            mu_pool = new_act(B, h, w, 32 * n_prog, E.device)
-            sc_pool = new_act(B, h, w, 32 * n_prog, E.device)
+            mu_pool = E.act(B, h, w, 32 * n_prog)
+            sc_pool = E.act(B, h, w, 32 * n_prog)
         kind, q = ChannelMask.mode_for(mask_pol, quality)
         mask_mode = {"ones": L.MASK_ONES, "zeros": L.MASK_ZEROS, "threshold": L.MASK_THRESHOLD}[kind]
         sps = self.support_progressive_slices
@@ -445,7 +461,7 @@ class ChannelProgresssiveWACNN(nn.Module):
             if self.all_scalable:
                 mu, scale = mu_pool.slice(32 * i, 32), sc_pool.slice(32 * i, 32)
             else:
-                mu, scale = new_act(B, h, w, 32, E.device), new_act(B, h, w, 32, E.device)
+                mu, scale = E.act(B, h, w, 32), E.act(B, h, w, 32)
             self._stack(E, P["cc_mean_transforms_prog"][i], mean_sup, mu)
             self._stack(E, P["cc_scale_transforms_prog"][i], scale_sup, scale)
             if self.all_scalable:  # bookkeeping only matters when the supports read these lists
@@ -463,7 +479,7 @@ class ChannelProgresssiveWACNN(nn.Module):
                     std_total.append(scale if self.support_std else mut)
                     mu_total.append(mut)
             thr = E.quantile_threshold(scale, q) if mask_mode == L.MASK_THRESHOLD else None
-            y_pre = new_act(B, h, w, 32, E.device)
+            y_pre = E.act(B, h, w, 32)
             code(i, mu, scale, mask_mode, thr, y_pre)
             out_i = y_hat_q.slice(32 * i, 32)
             if residual_before_lrp:  # forward_single_quality only (CHProg_cnn.py:1153-1164)
@@ -487,12 +503,13 @@ class ChannelProgresssiveWACNN(nn.Module):
 
     def _encoder_front(self, P, x: Tensor, enhanced: bool, want_z_lik: bool):
         E = P["eng"]
+        E.begin(0)
         y = self._g_a(P, x)
         z = self._h_a(P, y)
         B, hw_z = z.B, z.H * z.W
         z_sym = torch.empty((B, z.C * hw_z), dtype=torch.int32, device=E.device)
         z_idx = torch.empty((B, z.C * hw_z), dtype=torch.int32, device=E.device)
-        z_hat = new_act(B, z.H, z.W, z.C, E.device)
+        z_hat = E.act(B, z.H, z.W, z.C)
         E.bottleneck_quantize(z, P["medians"], z_sym, z_idx, z_hat)
         z_lik = E.bottleneck_likelihood(z_hat, P["eb_lik"]) if want_z_lik else None
         lm, ls = self._latents(P, z_hat, enhanced)
@@ -693,7 +710,7 @@ class ChannelProgresssiveWACNN(nn.Module):
                 st.wait_stream(cur)
                 with torch.cuda.device(dev), torch.cuda.stream(st), torch.no_grad():
                     outs[g] = self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, lo, hi, shape,
-                                                     quality, mask_pol)
+                                                     quality, mask_pol, slot=g + 1)
             except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
                 errs[g] = e
 
@@ -710,16 +727,18 @@ class ChannelProgresssiveWACNN(nn.Module):
             outs[g].record_stream(cur)
         return {"x_hat": torch.cat(outs, 0)}
 
-    def _decompress_group(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, quality, mask_pol):
+    def _decompress_group(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, quality, mask_pol,
+                          slot: int = 0):
         """Decode images [lo, hi) of a batch whose streams are laid out slice-major: stream (s, b) = s*B_total + b."""
         E: Engine = P["eng"]
         dev = E.device
+        E.begin(slot)
         B = hi - lo
         hz, wz = int(shape[0]), int(shape[1])
         Cz = self.entropy_bottleneck._quantized_cdf.size(0)
         z_idx = E.bottleneck_indexes(B, hz * wz, Cz)
         z_sym = _ans.decode_batch(z_data, z_off_dev[lo:hi + 1], z_idx, P["eb_tables"])
-        z_hat = new_act(B, hz, wz, Cz, dev)
+        z_hat = E.act(B, hz, wz, Cz)
         E.bottleneck_dequantize(z_sym, P["medians"], z_hat)
         lm, ls = self._latents(P, z_hat, enhanced=not (quality == 0))
         h, w = 4 * hz, 4 * wz
