@@ -77,6 +77,14 @@ int pcodec_rans_decode_batch(const uint8_t *in_bytes, const int64_t *in_offsets,
                              const int32_t *indexes, const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes,
                              const int32_t *offsets, int n_tables, int32_t *out_symbols, void *stream);
 
+/* Same decoder for streams that are NOT consecutive in in_bytes: stream s occupies bytes [starts[s], ends[s]).  Lets
+ * one launch decode several slices of a sub-batch (e.g. base slices 5..9, whose parameters do not depend on each
+ * other, CHProg_cnn.py:878) out of a slice-major stream container. */
+int pcodec_rans_decode_ranges(const uint8_t *in_bytes, const int64_t *starts, const int64_t *ends, int n_streams,
+                              int64_t n_per_stream, const int32_t *indexes, const int32_t *cdfs, int cdf_stride,
+                              const int32_t *cdf_sizes, const int32_t *offsets, int n_tables, int32_t *out_symbols,
+                              void *stream);
+
 /* HOST-only scalar walk over the same state arithmetic as the kernels (csrc/rans_core.h); exists so CPU unit
  * tests can pin that arithmetic against the oracle.  Not used by the product path.  Words are written at the END
  * of `words`; returns the number of words used or -1 on overflow. */

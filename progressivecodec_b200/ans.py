@@ -89,6 +89,22 @@ def decode_batch(data: torch.Tensor, offsets: torch.Tensor, indexes: torch.Tenso
     return out
 
 
+def decode_ranges(data: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor, indexes: torch.Tensor,
+                  tables: CdfTables) -> torch.Tensor:
+    """Like decode_batch for streams at arbitrary byte ranges [starts[s], ends[s]) of `data` (int64 CUDA tensors)."""
+    assert data.is_cuda and indexes.is_cuda and indexes.dtype == torch.int32 and indexes.dim() == 2
+    indexes = indexes.contiguous()
+    S, N = indexes.shape
+    starts, ends = starts.contiguous(), ends.contiguous()
+    assert starts.is_cuda and ends.is_cuda and starts.numel() == S and ends.numel() == S
+    out = torch.empty((S, N), dtype=torch.int32, device=indexes.device)
+    L.check(L.lib().pcodec_rans_decode_ranges(data.data_ptr(), starts.data_ptr(), ends.data_ptr(), S, N,
+                                              indexes.data_ptr(), tables.cdfs.data_ptr(), tables.cdfs.shape[1],
+                                              tables.sizes.data_ptr(), tables.offsets.data_ptr(), tables.cdfs.shape[0],
+                                              out.data_ptr(), _stream()), "rans_decode_ranges")
+    return out
+
+
 def pack_streams(strings: Sequence[bytes], device) -> Tuple[torch.Tensor, torch.Tensor]:
     """Host byte strings -> (uint8 CUDA blob with 8 bytes of zero slack, int64 CPU offsets)."""
     lens = [len(s) for s in strings]

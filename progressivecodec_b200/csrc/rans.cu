@@ -234,12 +234,13 @@ __device__ __forceinline__ int32_t dec_escape(uint64_t &x, WordReader &rd, int32
 constexpr int kDecThreads = 96;
 
 __global__ void __launch_bounds__(kDecThreads)
-rans_decode_kernel(const uint8_t *__restrict__ in_bytes, const int64_t *__restrict__ in_offsets, int n_streams,
+rans_decode_kernel(const uint8_t *__restrict__ in_bytes, const int64_t *__restrict__ in_starts,
+                   const int64_t *__restrict__ in_ends, int n_streams,
                    int64_t n, const int32_t *__restrict__ indexes, const int32_t *__restrict__ cdfs, int cdf_stride,
                    const int32_t *__restrict__ cdf_sizes, const int32_t *__restrict__ offsets,
                    int32_t *__restrict__ out_symbols) {
   __shared__ DecChunk buf[2];
-  __shared__ int32_t s_val[32];
+  __shared__ int32_t s_val[64];  // [0,32): decoded slot per symbol of the chunk; [32,64): dummy slots
   const int lane = threadIdx.x & 31;
   const int role = threadIdx.x >> 5;  // 0,1 = producers (symbols 0-15 / 16-31 of a chunk), 2 = walker
   const int s = blockIdx.x;
@@ -250,8 +251,7 @@ rans_decode_kernel(const uint8_t *__restrict__ in_bytes, const int64_t *__restri
   WordReader rd;
   uint64_t x = 0;
   if (role == 2) {
-    rd.init(reinterpret_cast<const uint32_t *>(in_bytes + in_offsets[s]),
-            (int32_t)((in_offsets[s + 1] - in_offsets[s]) / 4), lane);
+    rd.init(reinterpret_cast<const uint32_t *>(in_bytes + in_starts[s]), (int32_t)((in_ends[s] - in_starts[s]) / 4), lane);
     x = (uint64_t)rd.next();
     x |= (uint64_t)rd.next() << 32;
   }
@@ -313,10 +313,11 @@ rans_decode_kernel(const uint8_t *__restrict__ in_bytes, const int64_t *__restri
         const bool need_l = xc < kRansLower;
         if (need_l) xc = (xc << 32) | rd.nw;
         const bool rare_l = need_l || (st_l + fr_l) == 65536u;
-        uint32_t hi_l = (uint32_t)(xc >> 32) | (rare_l ? 0x80000000u : 0u);
-        if (valid) s_val[j] = lane;
-        const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, valid ? (uint32_t)xc : 0u);
-        const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, valid ? hi_l : 0u);
+        const uint32_t hi_l = (uint32_t)(xc >> 32) | (rare_l ? 0x80000000u : 0u);
+        const uint32_t vmask = 0u - (uint32_t)valid;     // branch-free select: all ones for the one right lane
+        s_val[valid ? j : 32 + lane] = lane;             // losers write to a private dummy slot (no divergence)
+        const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)xc & vmask);
+        const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, hi_l & vmask);
         if (__builtin_expect((int32_t)hi >= 0 && (hi | lo) != 0u, 1)) {
           x = ((uint64_t)hi << 32) | lo;  // common case: found in the window, no word consumed, not an escape
         } else {
@@ -412,7 +413,21 @@ extern "C" int pcodec_rans_decode_batch(const uint8_t *in_bytes, const int64_t *
   if (n_per_stream == 0) return PCODEC_OK;
   if (!indexes || !out_symbols) return PCODEC_ERR_BAD_ARG;
   rans_decode_kernel<<<n_streams, kDecThreads, 0, as_stream(stream)>>>(
-      in_bytes, in_offsets, n_streams, n_per_stream, indexes, cdfs, cdf_stride, cdf_sizes, offsets, out_symbols);
+      in_bytes, in_offsets, in_offsets + 1, n_streams, n_per_stream, indexes, cdfs, cdf_stride, cdf_sizes, offsets,
+      out_symbols);
+  PCODEC_RETURN_LAUNCH();
+}
+
+extern "C" int pcodec_rans_decode_ranges(const uint8_t *in_bytes, const int64_t *starts, const int64_t *ends,
+                                         int n_streams, int64_t n_per_stream, const int32_t *indexes,
+                                         const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes,
+                                         const int32_t *offsets, int n_tables, int32_t *out_symbols, void *stream) {
+  (void)n_tables;
+  if (n_streams <= 0 || n_per_stream < 0 || !in_bytes || !starts || !ends) return PCODEC_ERR_BAD_ARG;
+  if (n_per_stream == 0) return PCODEC_OK;
+  if (!indexes || !out_symbols) return PCODEC_ERR_BAD_ARG;
+  rans_decode_kernel<<<n_streams, kDecThreads, 0, as_stream(stream)>>>(
+      in_bytes, starts, ends, n_streams, n_per_stream, indexes, cdfs, cdf_stride, cdf_sizes, offsets, out_symbols);
   PCODEC_RETURN_LAUNCH();
 }
 

@@ -187,12 +187,18 @@ def pack_first_conv_im2col(m: nn.Conv2d, device, k_pad: int, name="") -> PackedC
     return PackedConv(packed, b, [(0, 0)], name=name)
 
 
-def pack_deconv_phases(m: nn.ConvTranspose2d, device, name="") -> List[PackedConv]:
+def pack_deconv_phases(m: nn.ConvTranspose2d, device, name="", pad_cout_to: int = 0) -> List[PackedConv]:
     """ConvTranspose2d k5 s2 p2 op1 [Cin,Cout,5,5] as 4 sub-pixel phases (py,px): output (2h+py, 2w+px) gathers
-    input (h+1-a, w+1-b) with kernel tap (py+2a, px+2b)."""
+    input (h+1-a, w+1-b) with kernel tap (py+2a, px+2b).  `pad_cout_to` zero-pads the output channels (the
+    3-channel image layer is padded to 16 so it can run on the tcgen05 kernel; callers read channels [0, Cout))."""
     assert m.kernel_size == (5, 5) and m.stride == (2, 2) and m.padding == (2, 2) and m.output_padding == (1, 1)
     w = m.weight.detach().to(device=device, dtype=torch.float32)  # [Cin, Cout, 5, 5]
     b = m.bias.detach().to(device=device, dtype=torch.float32) if m.bias is not None else None
+    if pad_cout_to and w.shape[1] < pad_cout_to:
+        extra = pad_cout_to - w.shape[1]
+        w = torch.cat([w, torch.zeros((w.shape[0], extra, 5, 5), dtype=w.dtype, device=device)], 1)
+        if b is not None:
+            b = torch.cat([b, torch.zeros(extra, dtype=b.dtype, device=device)])
     phases = []
     for py in (0, 1):
         for px in (0, 1):

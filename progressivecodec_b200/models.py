@@ -134,6 +134,7 @@ class ChannelProgresssiveWACNN(nn.Module):
         # execution knobs (not part of the reference API): tcgen05 path on/off, TF32 products per MAC in g_s
         self.tensor_cores = True
         self.synthesis_tf32_passes = 3
+        self.batch_independent_slices = True  # decode base slices 5..9 (mutually independent) as one phase
         self.decode_groups = 0          # 0 = auto (B // 4 capped at 4): image groups decoded on separate CUDA streams
         self._streams = None
 
@@ -220,7 +221,7 @@ class ChannelProgresssiveWACNN(nn.Module):
                     "g2": pack_gdn(seq[2], dev, f"{name}.2"), "d3": pack_deconv_phases(seq[3], dev, f"{name}.3"),
                     "g4": pack_gdn(seq[4], dev, f"{name}.4"), "w5": win(seq[5], f"{name}.5"),
                     "d6": pack_deconv_phases(seq[6], dev, f"{name}.6"), "g7": pack_gdn(seq[7], dev, f"{name}.7"),
-                    "d8": pack_deconv_phases(seq[8], dev, f"{name}.8")}
+                    "d8": pack_deconv_phases(seq[8], dev, f"{name}.8", pad_cout_to=16 if self.tensor_cores else 0)}
 
         def hyper_s(seq, name):
             return [pack_conv2d(seq[0], dev, f"{name}.0"), pack_conv2d(seq[2][0], dev, f"{name}.2.0"),
@@ -339,7 +340,7 @@ class ChannelProgresssiveWACNN(nn.Module):
             h = E.deconv_new(pk["d6"], h)
             h = E.gdn_new(pk["g7"], h, True)
             h = E.deconv_new(pk["d8"], h, L.EPI_CLAMP01 if clamp else L.EPI_LINEAR)
-            return E.to_nchw(h)
+            return E.to_nchw(h.slice(0, 3))  # the image layer may be zero-padded to 16 channels for the TC kernel
 
     def _h_a(self, P, y: Act) -> Act:
         E = P["eng"]
@@ -405,24 +406,51 @@ class ChannelProgresssiveWACNN(nn.Module):
         return out
 
     # -- the two slice loops -----------------------------------------------------------------------------------
-    def _base_slices(self, P, lm: Act, ls: Act, code):
+    def _base_slices(self, P, lm: Act, ls: Act, code, code_many=None):
         """Base loop (CHProg_cnn.py:507-544 / 729-764 / 874-904).  `code(i, mu, scale, y_pre)` performs the
-        quantise-or-decode step and must fill y_pre (= symbols + mu)."""
+        quantise-or-decode step and must fill y_pre (= symbols + mu).
+
+        Slice i is conditioned on the FIRST min(5, i) decoded slices only (`y_hat_slices[:indice]`, :731-735), so
+        from slice 5 on the entropy parameters no longer depend on the previous slice: when `code_many` is given
+        (decoder), slices 5..9 are coded as ONE phase — their parameter nets run back to back and all their
+        streams are entropy-decoded by a single launch — which removes 4 of the 10 serial stream-decode steps."""
         E = P["eng"]
         d0 = self.dimensions_M[0]
         B, h, w = lm.B, lm.H, lm.W
         y_hat_base = E.act(B, h, w, d0)
         lm0, ls0 = lm.slice(0, d0), ls.slice(0, d0)
-        for i in range(self.ns0):
-            k = min(self.max_support_slices, i)
-            sup = [y_hat_base.slice(0, 32 * k)] if k > 0 else []
+        mss = self.max_support_slices
+
+        def support(i):
+            k = min(mss, i)
+            return [y_hat_base.slice(0, 32 * k)] if k > 0 else []
+
+        def params(i):
+            sup = support(i)
             mu, scale = E.act(B, h, w, 32), E.act(B, h, w, 32)
             self._stack(E, P["cc_mean_transforms"][i], [lm0] + sup, mu)
             self._stack(E, P["cc_scale_transforms"][i], [ls0] + sup, scale)
+            return mu, scale
+
+        def refine(i, y_pre):
+            self._stack(E, P["lrp_transforms"][i], [lm0] + support(i) + [y_pre], y_hat_base.slice(32 * i, 32),
+                        L.EPI_LRP, r1=y_pre)
+
+        i = 0
+        while i < self.ns0:
+            if code_many is not None and mss >= 0 and i >= mss and self.ns0 - i > 1:
+                idxs = list(range(i, self.ns0))
+                ps = [params(j) for j in idxs]
+                y_pres = [E.act(B, h, w, 32) for _ in idxs]
+                code_many(idxs, [p[0] for p in ps], [p[1] for p in ps], y_pres)
+                for j, y_pre in zip(idxs, y_pres):
+                    refine(j, y_pre)
+                break
+            mu, scale = params(i)
             y_pre = E.act(B, h, w, 32)
             code(i, mu, scale, y_pre)
-            self._stack(E, P["lrp_transforms"][i], [lm0] + sup + [y_pre], y_hat_base.slice(32 * i, 32), L.EPI_LRP,
-                        r1=y_pre)
+            refine(i, y_pre)
+            i += 1
         return y_hat_base
 
     def _prog_slices(self, P, lm: Act, ls: Act, y_hat_base: Act, quality, mask_pol, code, mode: str,
@@ -752,8 +780,21 @@ class ChannelProgresssiveWACNN(nn.Module):
             sy = _ans.decode_batch(y_data, y_off_dev[s * B_total + lo:s * B_total + hi + 1], ind, tables)
             E.slice_dequantize(sy, mu, y_pre)
 
+        def decode_many(slices, mus, scales, y_pres):
+            k = len(slices)
+            ind = torch.empty((k * B, n), dtype=torch.int32, device=dev)
+            for j, scale in enumerate(scales):
+                E.slice_quantize(None, None, None, scale, L.MASK_ONES, None, table, bound, None, ind[j * B:(j + 1) * B],
+                                 None, None, None)
+            starts = torch.cat([y_off_dev[s * B_total + lo:s * B_total + hi] for s in slices])
+            ends = torch.cat([y_off_dev[s * B_total + lo + 1:s * B_total + hi + 1] for s in slices])
+            sy = _ans.decode_ranges(y_data, starts, ends, ind, tables)
+            for j, (mu, y_pre) in enumerate(zip(mus, y_pres)):
+                E.slice_dequantize(sy[j * B:(j + 1) * B], mu, y_pre)
+
         y_hat_base = self._base_slices(
-            P, lm, ls, lambda i, mu, scale, y_pre: decode_slice(i, scale, L.MASK_ONES, None, mu, y_pre))
+            P, lm, ls, lambda i, mu, scale, y_pre: decode_slice(i, scale, L.MASK_ONES, None, mu, y_pre),
+            code_many=decode_many if self.batch_independent_slices else None)
         if quality == 0:
             return self._g_s(P, y_hat_base, 0, clamp=True)
         y_hat_q = self._prog_slices(
