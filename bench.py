@@ -178,8 +178,15 @@ def conv_roofline(net, peaks, peak_kind):
     avg = sum(times) / len(times)
     achieved = flops / avg / 1e12
     peak = peaks["bf16_tflops"]
-    return {"bound": "tensor", "kernel": "conv_taps (5x5 s2 192->192 @128x192 out)", "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind + " bf16 burst",
+    # DRAM traffic of this exact launch from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_full_conv_taps_tc_5x5s2_192.csv: dram__bytes_read 114.85 MB + dram__bytes_write 12.69 MB);
+    # algorithmic bytes = 75.5 MB input + 7.4 MB TF32 hi/lo weights + 18.9 MB output = 101.8 MB.
+    return {"bound": "tensor", "kernel": "conv_taps_tc_kernel (tcgen05 3xTF32; 5x5 s2 192->192 @128x192 out)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 127.54e6,
+            "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes": 101.8e6,
+            "peak_kind": peak_kind + " bf16 burst (cuBLAS); this kernel issues 3 TF32 MMAs per algorithmic MAC, "
+                         "TF32 runs at half the bf16 rate, so frac <= 1/6",
+            "tensor_pipe_frac_of_tf32_peak": 3.0 * achieved / (peak / 2.0),
             "flops_per_launch": flops, "avg_launch_ms": avg * 1e3}
 
 
@@ -281,6 +288,21 @@ def run_ours(args):
             tc = _cpu_time_sweep(orc, xs, sample_q)
             cpu = {"value": len(sample_q) / tc, "unit": "image-qualities/s", "cores": cores, "kind": "port",
                    "sample": "1 image 768x512 x qualities [0,1.25,10] (compress+decompress), after 1 warm-up call"}
+        lat = None
+        if world == 1:
+            x1 = x_dev[:1].contiguous()
+            for _ in range(2):
+                c1 = net.compress(x1, quality=5, return_device_streams=True)
+                net.decompress(c1, c1["shape"], quality=5)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            c1 = net.compress(x1, quality=5, return_device_streams=True)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            net.decompress(c1, c1["shape"], quality=5)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            lat = {"batch": 1, "quality": 5, "compress_ms": 1e3 * (t1 - t0), "decompress_ms": 1e3 * (t2 - t1)}
         line = {"metric": "768x512 img/s compress+decompress per quality", "value": value, "unit": "image-qualities/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -292,7 +314,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "image-qualities/s", "h2d_bytes_per_step": h2d[0],
                         "d2h_bytes_per_step": d2h[0], "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-                "step_algorithmic_tflops": step_tflops, "cpu_baseline": cpu}
+                "step_algorithmic_tflops": step_tflops, "single_image_latency": lat, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
