@@ -5,18 +5,22 @@
 //   * B (weights, K-major [Cout][T*Cin] fp32, pre-split on the host into TF32 hi and lo parts) arrives by TMA
 //     (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage ring; OOB columns of the last slab are
 //     zero-filled by the TMA unit.
-//   * A (activations) is an on-the-fly gather of the shifted NHWC patch (padding / stride / virtual concat /
-//     x*x for GDN handled in the address math), so four producer warps load it with coalesced 128-bit LDGs, split
-//     every value into hi = tf32 part and lo = x - hi, and store both in the canonical SWIZZLE_128B K-major
-//     layout the UMMA descriptors expect (16-byte chunk index XOR (row & 7)).
-//   * One elected thread issues tcgen05.mma.kind::tf32: acc += Ahi*Bhi + Alo*Bhi + Ahi*Blo (fp32 accumulator in
-//     TMEM). The dropped Alo*Blo term is ~2^-22 relative, i.e. fp32-class accuracy, which the codec needs because
-//     these outputs feed round(), sigma->CDF-index thresholds and the quantile ranking.
-//     `tc_split = 1` issues only the first product (plain TF32) — used for the synthesis transform g_s, whose
-//     output only enters PSNR.
-//   * tcgen05.commit releases ring slots and finally signals the epilogue; the producer warps then read the
-//     accumulator with tcgen05.ld (one TMEM lane = one output pixel per thread), apply the fused epilogue
-//     (bias / GELU / residual / gate / GDN / LRP / clamp / pixel-shuffle) and store 64-byte runs per thread.
+//   * A (activations) is an on-the-fly gather of the shifted NHWC patch (padding / stride / virtual concat in the
+//     address math).  Four loader warps copy it with 16-byte cp.async (LDGSTS, zero-fill for padding) into a
+//     shared-memory staging tile; four converter warps read one tile ROW per thread, form lo = x - trunc_tf32(x)
+//     (and x*x for GDN) and write hi (= the raw fp32: kind::tf32 ignores the low 13 mantissa bits, verified) and
+//     lo with tcgen05.st into a double-buffered A operand area of TENSOR MEMORY.
+//   * One elected thread issues tcgen05.mma.kind::tf32 in the TS form (A from TMEM, B from shared memory):
+//     acc += Ahi*Bhi ; acc_lo += Alo*Bhi + Ahi*Blo.  A in TMEM matters: in the SS form the operand fetch from
+//     shared memory (~64 B/clk) re-read the 4 KB A tile for every one of the 3 products and capped the kernel at
+//     ~43 % of the MMA rate for N = 96 (measured: time per MMA == (A bytes + B bytes)/64).
+//     The dropped Alo*Blo term is ~2^-22 relative, i.e. fp32-class accuracy, which the codec needs because these
+//     outputs feed round(), sigma->CDF-index thresholds and the quantile ranking.
+//     `tc_split = 1` issues only the first product (plain TF32) — for layers whose output only enters PSNR.
+//   * tcgen05.commit releases ring slots / A buffers and finally signals the epilogue; all eight producer warps
+//     then read the accumulators with tcgen05.ld (one TMEM lane = one output pixel per thread), sum the partial
+//     accumulators, apply the fused epilogue (bias / GELU / residual / gate / GDN / LRP / clamp / pixel-shuffle)
+//     and store 64-byte runs per thread.
 // The K order (segment, tap, channel slab; hi*hi, lo*hi, hi*lo) is fixed: deterministic and batch invariant.
 #include <cuda.h>
 
@@ -33,7 +37,7 @@ constexpr int TC_BK = 32;                  // fp32 elements per K slab = 128 byt
 constexpr int TC_A_BYTES = TC_BM * 128;    // one A tile (hi or lo)
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = 32 * (TC_PRODUCER_WARPS + 2);  // warps 0-7: A producers + epilogue, warp 8: TMA + TMEM alloc, warp 9: MMA
-constexpr int TC_SMEM_LIMIT = 220 * 1024;
+constexpr int TC_SMEM_LIMIT = 225 * 1024;
 
 struct TcWeights {
   CUtensorMap map_hi, map_lo;
@@ -45,6 +49,7 @@ struct TcParams {
   pcodec_conv_desc d;
   int64_t M;
   int bn, stages, split, n_steps;
+  int raw_stages;  // unused (kept for layout stability)
   int n_hi_acc;  // TMEM accumulators for the hi*hi products (round-robin over K slabs); +1 for the lo terms when split
 };
 
@@ -86,6 +91,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       : "memory");
 }
 
+// 16-byte async copy global -> shared (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on an mbarrier once all prior cp.async of this thread have landed (does not bump the pending count)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -105,6 +119,34 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (TS form): A = 128 lanes x 8 columns of fp32 at tmem_a
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: this thread's lane, 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const float4 (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(addr),
+      "r"(__float_as_uint(v[0].x)), "r"(__float_as_uint(v[0].y)), "r"(__float_as_uint(v[0].z)), "r"(__float_as_uint(v[0].w)),
+      "r"(__float_as_uint(v[1].x)), "r"(__float_as_uint(v[1].y)), "r"(__float_as_uint(v[1].z)), "r"(__float_as_uint(v[1].w)),
+      "r"(__float_as_uint(v[2].x)), "r"(__float_as_uint(v[2].y)), "r"(__float_as_uint(v[2].z)), "r"(__float_as_uint(v[2].w)),
+      "r"(__float_as_uint(v[3].x)), "r"(__float_as_uint(v[3].y)), "r"(__float_as_uint(v[3].z)), "r"(__float_as_uint(v[3].w)),
+      "r"(__float_as_uint(v[4].x)), "r"(__float_as_uint(v[4].y)), "r"(__float_as_uint(v[4].z)), "r"(__float_as_uint(v[4].w)),
+      "r"(__float_as_uint(v[5].x)), "r"(__float_as_uint(v[5].y)), "r"(__float_as_uint(v[5].z)), "r"(__float_as_uint(v[5].w)),
+      "r"(__float_as_uint(v[6].x)), "r"(__float_as_uint(v[6].y)), "r"(__float_as_uint(v[6].z)), "r"(__float_as_uint(v[6].w)),
+      "r"(__float_as_uint(v[7].x)), "r"(__float_as_uint(v[7].y)), "r"(__float_as_uint(v[7].z)), "r"(__float_as_uint(v[7].w))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -161,29 +203,34 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   const int bn = P.bn, stages = P.stages;
   const bool split = P.split == 3;
   const int b_bytes = bn * 128;
-  const int stage_bytes = (split ? 2 : 1) * (TC_A_BYTES + b_bytes);
+  const int stage_bytes = TC_A_BYTES + (split ? 2 : 1) * b_bytes;  // raw A staging tile | B_hi | (B_lo)
 
   // 1024-byte aligned carve-up
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  auto a_hi = [&](int s) { return smem_base + s * stage_bytes; };
-  auto a_lo = [&](int s) { return smem_base + s * stage_bytes + TC_A_BYTES; };
-  auto b_hi = [&](int s) { return smem_base + s * stage_bytes + (split ? 2 : 1) * TC_A_BYTES; };
+  auto a_raw = [&](int s) { return smem_base + s * stage_bytes; };
+  auto b_hi = [&](int s) { return smem_base + s * stage_bytes + TC_A_BYTES; };
   auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
   const uint32_t bar_base = smem_base + stages * stage_bytes;
-  auto full_a = [&](int s) { return bar_base + 8u * s; };
-  auto full_b = [&](int s) { return bar_base + 8u * (stages + s); };
-  auto empty = [&](int s) { return bar_base + 8u * (2 * stages + s); };
-  const uint32_t tmem_full = bar_base + 8u * (3 * stages);
+  auto raw_full = [&](int s) { return bar_base + 8u * s; };                   // cp.async landed        (128 loaders)
+  auto raw_empty = [&](int s) { return bar_base + 8u * (stages + s); };       // staging tile consumed  (128 converters)
+  auto full_b = [&](int s) { return bar_base + 8u * (2 * stages + s); };      // TMA bytes landed
+  auto empty_b = [&](int s) { return bar_base + 8u * (3 * stages + s); };     // MMAs that read B done  (tcgen05.commit)
+  auto a_full = [&](int q) { return bar_base + 8u * (4 * stages + q); };      // A operand in TMEM      (128 converters)
+  auto a_empty = [&](int q) { return bar_base + 8u * (4 * stages + 2 + q); }; // MMAs that read it done (tcgen05.commit)
+  const uint32_t tmem_full = bar_base + 8u * (4 * stages + 4);
   const uint32_t tmem_slot = tmem_full + 8u;
   uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
 
-  // TMEM accumulators: the tensor core's fp32 accumulate truncates (round-toward-zero) once per MMA, so the error
-  // grows linearly with the number of MMAs that touch an accumulator.  The small lo*hi / hi*lo products therefore
-  // get their own accumulator (their truncation error is 2^-11 smaller in absolute terms), and the hi*hi
-  // products round-robin over n_hi_acc accumulators; the epilogue sums them with round-to-nearest adds.
+  // TMEM layout: [n_acc accumulators of bn columns][2 A-operand buffers of a_cols columns].
+  // Accumulators: the tensor core's fp32 accumulate truncates (round-toward-zero) once per MMA, so the error grows
+  // linearly with the number of MMAs that touch an accumulator.  The small lo*hi / hi*lo products therefore get
+  // their own accumulator (their truncation error is 2^-11 smaller in absolute terms), and the hi*hi products
+  // round-robin over n_hi_acc accumulators; the epilogue sums them with round-to-nearest adds.
   const int n_acc = P.n_hi_acc + (split ? 1 : 0);
+  const int a_cols = split ? 64 : 32;            // hi (32 fp32 columns) + lo (32)
+  const uint32_t a_tmem_off = (uint32_t)(n_acc * bn);
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < n_acc * bn) tmem_cols <<= 1;
+  while ((int)tmem_cols < n_acc * bn + 2 * a_cols) tmem_cols <<= 1;
 
   __shared__ int s_dy[PCODEC_MAX_TAPS], s_dx[PCODEC_MAX_TAPS];
   __shared__ const float *s_seg_ptr[PCODEC_MAX_SEGMENTS];
@@ -201,9 +248,14 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 
   if (warp == TC_PRODUCER_WARPS + 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_a(s), 128);  // one 4-warp producer group per slab
+      mbar_init(raw_full(s), 128);
+      mbar_init(raw_empty(s), 128);
       mbar_init(full_b(s), 1);
-      mbar_init(empty(s), 1);
+      mbar_init(empty_b(s), 1);
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(a_full(q), 128);
+      mbar_init(a_empty(q), 1);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -220,120 +272,101 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 
   if (warp < TC_PRODUCER_WARPS) {
     // =============================== A producers ===============================
-    // Two groups of 4 warps alternate K slabs (group g builds slabs g, g+2, ...), so each group has two slab
-    // times to gather, split and store its 128x32 tile; inside a group a lane owns one 16-byte chunk (lane & 7)
-    // of 8 rows and keeps the loads of its next two slabs in flight (three rotating register buffers, loop
-    // unrolled by 3 so the rotation costs no moves).  Per-row state is a 32-bit pixel index; a tap only adds a
-    // uniform pixel offset, so changing tap costs one 64-bit multiply-add per row.
-    constexpr int RPT = 8;       // rows per thread
-    const int grp = warp >> 2, gw = warp & 3;
-    const int chunk = lane & 7;  // 16-byte chunk inside the 128-byte slab row
-    const int sub = lane >> 3;
-    int pix0[RPT];               // pixel index of (n, h*in_step, w*in_step) in the input image stack
-    int ih0[RPT], iw0[RPT];      // ih0 = INT_MIN/2 marks a row beyond M (never valid)
-    uint32_t soff[RPT];          // swizzled byte offset of (row, chunk) inside an A tile
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      const int row = gw * 32 + i * 4 + sub;
-      const int64_t m = m0 + row;
-      const bool okr = m < P.M;
-      const int64_t mm = okr ? m : 0;
-      const int w = (int)(mm % d.grid_w);
-      const int64_t t = mm / d.grid_w;
-      const int h = (int)(t % d.grid_h);
-      const int n = (int)(t / d.grid_h);
-      ih0[i] = okr ? h * d.in_step : -(1 << 28);
-      iw0[i] = w * d.in_step;
-      pix0[i] = (n * d.in_h + h * d.in_step) * d.in_w + w * d.in_step;
-      soff[i] = row * 128 + ((chunk ^ (row & 7)) << 4);
-    }
-    const bool square = (d.flags & PCODEC_FLAG_SQUARE_INPUT) != 0;
-    const int in_h = d.in_h, in_w = d.in_w, n_taps = d.n_taps, n_segments = d.n_segments;
-    int seg = 0, tap = 0, kc = 0;  // kc: 32-channel slab inside the segment
-    const float *rowptr[RPT];
-    uint32_t rowmask = 0;          // bit i: row i reads real data for the current tap
-    int seg_slabs = 0, seg_channels = 0;
-    auto retarget = [&]() {        // (seg, tap) changed: recompute the per-row source pointers
-      const float *base = s_seg_ptr[seg] + chunk * 4;
-      const int ps = s_seg_ps[seg];
-      const int dy = s_dy[tap], dx = s_dx[tap];
-      const int tapoff = dy * in_w + dx;
-      seg_channels = s_seg_ch[seg];
-      seg_slabs = (seg_channels + TC_BK - 1) / TC_BK;
-      rowmask = 0;
+    if (warp < 4) {
+      // ------------------------------- loaders (warps 0-3) -------------------------------
+      // 16-byte cp.async of the shifted patch into the slot's staging tile, 128-byte-swizzled ([row][chunk ^ row&7])
+      // so that the converters' row-wise reads are bank-conflict free.  A lane owns chunk (lane & 7) of 8 rows.
+      constexpr int RPT = 8;
+      const int chunk = lane & 7, sub = lane >> 3;
+      uint32_t soff[RPT];
+      int pix0[RPT], ih0[RPT], iw0[RPT];
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        const bool v = (unsigned)(ih0[i] + dy) < (unsigned)in_h && (unsigned)(iw0[i] + dx) < (unsigned)in_w;
-        rowptr[i] = base + (int64_t)(v ? pix0[i] + tapoff : 0) * ps;
-        rowmask |= (v ? 1u : 0u) << i;
+        const int r = warp * 32 + i * 4 + sub;
+        soff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
+        const int64_t m = m0 + r;
+        const bool okr = m < P.M;
+        const int64_t mm = okr ? m : 0;
+        const int w = (int)(mm % d.grid_w);
+        const int64_t t = mm / d.grid_w;
+        const int h = (int)(t % d.grid_h);
+        const int n = (int)(t / d.grid_h);
+        ih0[i] = okr ? h * d.in_step : -(1 << 28);
+        iw0[i] = w * d.in_step;
+        pix0[i] = (n * d.in_h + h * d.in_step) * d.in_w + w * d.in_step;
       }
-    };
-    auto advance2 = [&]() {        // step the (seg, tap, kc) iterator by two slabs
+      const int in_h = d.in_h, in_w = d.in_w, n_taps = d.n_taps;
+      int seg = 0, tap = 0, st = 0;
+      uint32_t eph = 1;  // parity to wait for on raw_empty
+      for (int s = 0; s < n_steps;) {
+        const float *base = s_seg_ptr[seg] + chunk * 4;
+        const int ps = s_seg_ps[seg], seg_channels = s_seg_ch[seg];
+        const int seg_slabs = (seg_channels + TC_BK - 1) / TC_BK;
+        const int dy = s_dy[tap], dx = s_dx[tap];
+        const int tapoff = dy * in_w + dx;
+        const float *rowptr[RPT];
+        uint32_t rowmask = 0;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (++kc == seg_slabs) {
-          kc = 0;
-          if (++tap == n_taps) { tap = 0; ++seg; }
-          if (seg < n_segments) retarget();
+        for (int i = 0; i < RPT; ++i) {
+          const bool v = (unsigned)(ih0[i] + dy) < (unsigned)in_h && (unsigned)(iw0[i] + dx) < (unsigned)in_w;
+          rowptr[i] = base + (int64_t)(v ? pix0[i] + tapoff : 0) * ps;
+          rowmask |= (v ? 1u : 0u) << i;
         }
-      }
-    };
-    auto fetch = [&](float4 (&v)[RPT]) {
-      const int c = kc * TC_BK + chunk * 4;
-      const bool c_ok = c < seg_channels;
-      const uint32_t mask = c_ok ? rowmask : 0u;
+        for (int kc = 0; kc < seg_slabs; ++kc, ++s) {
+          mbar_wait(raw_empty(st), eph);
+          const uint32_t dst = a_raw(st);
+          const uint32_t mask = (kc * TC_BK + chunk * 4 < seg_channels) ? rowmask : 0u;
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((mask >> i) & 1u) x = __ldg(reinterpret_cast<const float4 *>(rowptr[i] + kc * TC_BK));
-        v[i] = x;
+          for (int i = 0; i < RPT; ++i)
+            cp_async16(dst + soff[i], rowptr[i] + kc * TC_BK, ((mask >> i) & 1u) ? 16u : 0u);
+          cp_async_arrive_noinc(raw_full(st));
+          if (++st == stages) { st = 0; eph ^= 1u; }
+        }
+        if (++tap == n_taps) { tap = 0; ++seg; }
       }
-      advance2();
-    };
-    int st = grp % stages;                 // ring slot of this group's current slab
-    uint32_t ph = ((grp / stages) & 1) ^ 1; // parity to wait for on `empty`
-    uint8_t *a_tiles = smem_gen;           // generic pointer to stage 0
-    auto produce = [&](float4 (&v)[RPT]) {
-      mbar_wait(empty(st), ph);
-      uint8_t *hi_base = a_tiles + (size_t)st * stage_bytes;
-      uint8_t *lo_base = hi_base + TC_A_BYTES;
+    } else {
+      // ------------------------------- converters (warps 4-7) -------------------------------
+      // Thread = tile row (TMEM lane) 32*(warp & 3) + lane: read the row's 32 floats from the staging tile, write
+      // hi (raw; the MMA truncates) and lo = x - trunc_tf32(x) into the A operand buffer of tensor memory.
+      const bool square = (d.flags & PCODEC_FLAG_SQUARE_INPUT) != 0;
+      const int arow = (warp & 3) * 32 + lane;
+      const uint32_t row_off = arow * 128, row_x = (uint32_t)(arow & 7);
+      const uint32_t lane_base = tmem_acc + a_tmem_off + ((uint32_t)((warp & 3) * 32) << 16);
+      int st = 0, q = 0;
+      uint32_t ph = 0, qph = 1;
+      for (int s = 0; s < n_steps; ++s) {
+        mbar_wait(raw_full(st), ph);
+        const uint8_t *src = smem_gen + (size_t)st * stage_bytes + row_off;
+        float4 x[8];
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        float4 x = v[i];
-        if (square) { x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w; }
+        for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4 *>(src + (((uint32_t)c ^ row_x) << 4));
+        mbar_arrive(raw_empty(st));  // staging tile consumed (values are in registers)
+        if (square) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { x[c].x *= x[c].x; x[c].y *= x[c].y; x[c].z *= x[c].z; x[c].w *= x[c].w; }
+        }
+        mbar_wait(a_empty(q), qph);  // MMAs that read this A buffer two slabs ago have retired
+        tc_fence_after();
+        const uint32_t ta = lane_base + (uint32_t)(q * a_cols);
+        tmem_st32(ta, x);
         if (split) {
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-          *reinterpret_cast<float4 *>(hi_base + soff[i]) = h;
-          *reinterpret_cast<float4 *>(lo_base + soff[i]) = l;
-        } else {
-          *reinterpret_cast<float4 *>(hi_base + soff[i]) = x;
+          float4 l[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            l[c].x = x[c].x - __uint_as_float(__float_as_uint(x[c].x) & 0xFFFFE000u);
+            l[c].y = x[c].y - __uint_as_float(__float_as_uint(x[c].y) & 0xFFFFE000u);
+            l[c].z = x[c].z - __uint_as_float(__float_as_uint(x[c].z) & 0xFFFFE000u);
+            l[c].w = x[c].w - __uint_as_float(__float_as_uint(x[c].w) & 0xFFFFE000u);
+          }
+          tmem_st32(ta + 32u, l);
         }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_full(q));
+        if (++st == stages) { st = 0; ph ^= 1u; }
+        q ^= 1;
+        if (q == 0) qph ^= 1u;
       }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(full_a(st));
-      st += 2;                   // next slab of this group is two ring slots further
-      while (st >= stages) { st -= stages; ph ^= 1u; }
-    };
-    retarget();
-    if (grp == 1) {  // group 1 starts at slab 1
-      if (++kc == seg_slabs) { kc = 0; if (++tap == n_taps) { tap = 0; ++seg; } if (seg < n_segments) retarget(); }
-    }
-    float4 b0[RPT], b1[RPT], b2[RPT];
-    if (grp < n_steps) fetch(b0);
-    if (grp + 2 < n_steps) fetch(b1);
-    for (int s = grp; s < n_steps; s += 6) {
-      if (s + 4 < n_steps) fetch(b2);
-      produce(b0);
-      if (s + 2 >= n_steps) break;
-      if (s + 6 < n_steps) fetch(b0);
-      produce(b1);
-      if (s + 4 >= n_steps) break;
-      if (s + 8 < n_steps) fetch(b1);
-      produce(b2);
     }
 
     // =============================== epilogue ===============================
@@ -406,7 +439,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
       uint32_t ph = 1;
       for (int s = 0; s < n_steps; ++s, ++st) {
         if (st == stages) { st = 0; ph ^= 1u; }
-        mbar_wait(empty(st), ph);
+        mbar_wait(empty_b(st), ph);
         const int k = tap * d.cin_total + seg_cbase + kc * TC_BK;
         mbar_expect_tx(full_b(st), (uint32_t)((split ? 2 : 1) * b_bytes));
         tma_load_2d(b_hi(st), &map_hi, full_b(st), k, n0);
@@ -423,29 +456,34 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     if (lane == 0) {
       // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int st = 0, hi_idx = 0;
-      uint32_t ph = 0;
-      for (int s = 0; s < n_steps; ++s, ++st, ++hi_idx) {
-        if (st == stages) { st = 0; ph ^= 1u; }
-        if (hi_idx == P.n_hi_acc) hi_idx = 0;
-        mbar_wait(full_a(st), ph);
+      int st = 0, hi_idx = 0, q = 0;
+      uint32_t ph = 0, qph = 0;
+      const uint32_t acc_lo = tmem_acc + (uint32_t)(P.n_hi_acc * bn);
+      for (int s = 0; s < n_steps; ++s) {
+        mbar_wait(a_full(q), qph);
         mbar_wait(full_b(st), ph);
         tc_fence_after();
-        const uint64_t da_hi = umma_desc_sw128(a_hi(st)), db_hi = umma_desc_sw128(b_hi(st));
-        const uint64_t da_lo = umma_desc_sw128(a_lo(st)), db_lo = umma_desc_sw128(b_lo(st));
+        const uint64_t db_hi = umma_desc_sw128(b_hi(st)), db_lo = umma_desc_sw128(b_lo(st));
+        const uint32_t ta_hi = tmem_acc + a_tmem_off + (uint32_t)(q * a_cols);
+        const uint32_t ta_lo = ta_hi + 32u;
         const uint32_t acc_hi = tmem_acc + (uint32_t)(hi_idx * bn);
-        const uint32_t acc_lo = tmem_acc + (uint32_t)(P.n_hi_acc * bn);
         const bool first_hi = s < P.n_hi_acc;  // first slab that touches this hi accumulator
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t adv = (uint64_t)(k * 2);  // 8 tf32 = 32 bytes = 2 x 16-byte units inside the swizzle row
-          umma_tf32(acc_hi, da_hi + adv, db_hi + adv, idesc, (!first_hi || k > 0) ? 1u : 0u);
+          const uint64_t adv = (uint64_t)(k * 2);  // B: 8 tf32 = 32 bytes = 2 x 16-byte units inside the swizzle row
+          const uint32_t ak = (uint32_t)(k * 8);   // A: 8 fp32 columns of tensor memory
+          umma_tf32_ts(acc_hi, ta_hi + ak, db_hi + adv, idesc, (!first_hi || k > 0) ? 1u : 0u);
           if (split) {
-            umma_tf32(acc_lo, da_lo + adv, db_hi + adv, idesc, (s > 0 || k > 0) ? 1u : 0u);
-            umma_tf32(acc_lo, da_hi + adv, db_lo + adv, idesc, 1u);
+            umma_tf32_ts(acc_lo, ta_lo + ak, db_hi + adv, idesc, (s > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_ts(acc_lo, ta_hi + ak, db_lo + adv, idesc, 1u);
           }
         }
-        umma_commit(empty(st));  // implies tcgen05.fence::before_thread_sync
+        umma_commit(empty_b(st));  // B slot reusable once these MMAs retire (implies tcgen05.fence::before_thread_sync)
+        umma_commit(a_empty(q));   // A operand buffer reusable
+        if (++st == stages) { st = 0; ph ^= 1u; }
+        if (++hi_idx == P.n_hi_acc) hi_idx = 0;
+        q ^= 1;
+        if (q == 0) qph ^= 1u;
       }
       umma_commit(tmem_full);
     }
@@ -500,7 +538,7 @@ __global__ void split_weights_kernel(const float *__restrict__ w_tap_major, int 
 // result at fp32-class accuracy (measured: rms 1e-5 -> 3e-6 at K = 4800).
 int pick_bn(int cout, int k_total) {
   if (cout % 16 != 0) return 0;
-  int cap = k_total >= 1024 ? 128 : 256;
+  int cap = k_total >= 1024 ? 128 : 192;  // 2 accumulators x 192 + 128 A-operand columns = 512 TMEM columns
   if (const char *e = getenv("PCODEC_TC_BNCAP")) cap = atoi(e);  // experiment knob
   int fallback = 0;
   for (int tiles = 1; tiles <= 16; ++tiles) {
@@ -589,25 +627,31 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   int n_steps = 0;
   for (int s = 0; s < desc->n_segments; ++s) n_steps += desc->n_taps * ((desc->seg[s].channels + TC_BK - 1) / TC_BK);
   P.n_steps = n_steps;
-  const int stage_bytes = (P.split == 3 ? 2 : 1) * (TC_A_BYTES + h->bn * 128);
-  int stages = (TC_SMEM_LIMIT - 2048) / stage_bytes;
-  if (stages > 6) stages = 6;
+  const bool split3 = P.split == 3;
+  const int stage_bytes = TC_A_BYTES + (split3 ? 2 : 1) * h->bn * 128;  // raw A staging tile | B_hi | (B_lo)
+  auto need = [&](int st) { return st * stage_bytes + 1024 + 8 * (4 * st + 6) + 64; };
+  int stages = 2;
+  while (need(stages + 1) <= TC_SMEM_LIMIT && stages < 8) ++stages;
   if (const char *e = getenv("PCODEC_TC_STAGES")) stages = std::min(stages, atoi(e));  // experiment knob
   if (stages > n_steps) stages = n_steps;
-  if (stages < 1) return PCODEC_ERR_UNSUPPORTED;
+  if (stages < 1 || need(stages) > TC_SMEM_LIMIT) return PCODEC_ERR_UNSUPPORTED;
   P.stages = stages;
+  P.raw_stages = 0;
   {
-    int n_hi = 512 / h->bn - (P.split == 3 ? 1 : 0);
+    // TMEM columns: n_acc accumulators of bn + two A operand buffers (hi 32 [+ lo 32] columns each)
+    const int a_cols = split3 ? 64 : 32;
+    int n_acc = (512 - 2 * a_cols) / h->bn;
+    int n_hi = n_acc - (split3 ? 1 : 0);
     if (n_hi > 4) n_hi = 4;
     if (n_hi > n_steps) n_hi = n_steps;
-    if (n_hi < 1) n_hi = 1;
+    if (n_hi < 1) return PCODEC_ERR_UNSUPPORTED;
     P.n_hi_acc = n_hi;
   }
-  const int smem = stages * stage_bytes + 1024 /*align*/ + 8 * (3 * stages + 2) + 64;
+  const int smem = need(stages);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT + 4096);
+    attr_err = cudaFuncSetAttribute(conv_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
   });
   if (attr_err != cudaSuccess) return -(int)attr_err;
   dim3 grid((unsigned)ceil_div64(P.M, TC_BM), (unsigned)h->n_tiles);
