@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -35,8 +36,8 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                  // fp32 elements per K slab = 128 bytes = one swizzle row
 constexpr int TC_A_BYTES = TC_BM * 128;    // one A tile (hi or lo)
-constexpr int TC_PRODUCER_WARPS = 8;
-constexpr int TC_THREADS = 32 * (TC_PRODUCER_WARPS + 2);  // warps 0-7: A producers + epilogue, warp 8: TMA + TMEM alloc, warp 9: MMA
+constexpr int TC_PRODUCER_WARPS = 12;  // 4 loader warps + 2 groups of 4 converter warps
+constexpr int TC_THREADS = 32 * (TC_PRODUCER_WARPS + 2);  // warps 0-11: A producers + epilogue, warp 12: TMA + TMEM alloc, warp 13: MMA issuer
 constexpr int TC_SMEM_LIMIT = 225 * 1024;
 
 struct TcWeights {
@@ -49,8 +50,9 @@ struct TcParams {
   pcodec_conv_desc d;
   int64_t M;
   int bn, stages, split, n_steps;
-  int raw_stages;  // unused (kept for layout stability)
+  int raw_stages;  // debug knob bits (PCODEC_TC_DEBUG): 1 = skip A global loads, 2 = skip B TMA loads, 4 = skip converter TMEM stores
   int n_hi_acc;  // TMEM accumulators for the hi*hi products (round-robin over K slabs); +1 for the lo terms when split
+  int a_ring;    // depth of the A operand ring in tensor memory (2..4)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -98,6 +100,42 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 // arrive on an mbarrier once all prior cp.async of this thread have landed (does not bump the pending count)
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `n` of this thread's most recent cp.async groups are still in flight (n is warp-uniform, 0..3)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
+// One lane polls the barrier, the warp converges behind it: an mbarrier op per THREAD (128 try_waits + 128 arrives
+// per barrier per K slab) serialises in the shared-memory unit and was the whole per-slab cost of the v5 pipeline
+// (measured: ~1200 clk per slab with every load, TMEM store and 2 of 3 MMAs removed).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// one lane of a CONVERGED warp (PTX elect.sync): lets ptxas emit the single-thread tcgen05 instructions straight-line
+// instead of wrapping each in an ELECT / BRA.U.ANY loop (what `if (lane == 0)` compiles to)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
@@ -191,9 +229,31 @@ __device__ __forceinline__ float tc_epilogue(int epi, float acc, float r1, float
   }
 }
 
+// four channels at once, ONE switch: keeps a single copy of every transcendental in the kernel image (the code is
+// fetched cold by every CTA; 16 inlined copies of the scalar switch made the kernel 160 KB of SASS)
+__device__ __noinline__ float4 tc_epilogue4(int epi, float4 v, float4 r1, float4 r2, bool has_r2) {
+  float4 o;
+  o.x = tc_epilogue(epi, v.x, r1.x, r2.x, has_r2);
+  o.y = tc_epilogue(epi, v.y, r1.y, r2.y, has_r2);
+  o.z = tc_epilogue(epi, v.z, r1.z, r2.z, has_r2);
+  o.w = tc_epilogue(epi, v.w, r1.w, r2.w, has_r2);
+  return o;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------
+// Debug timeline (PCODEC_TC_DEBUG bit 6): CTA (0,0) records clock64() at pipeline events of its first 128 slabs.
+constexpr int TC_TRACE_SLABS = 128, TC_TRACE_EVENTS = 12;
+__device__ long long g_tc_trace[TC_TRACE_SLABS * TC_TRACE_EVENTS + 32];
+#define TC_TRACE(slab, ev)                                                                        \
+  do {                                                                                            \
+    if (trace && (slab) < TC_TRACE_SLABS) g_tc_trace[(slab) * TC_TRACE_EVENTS + (ev)] = clock64(); \
+  } while (0)
+#define TC_TRACE_G(ev)                                                                \
+  do {                                                                                \
+    if (trace) g_tc_trace[TC_TRACE_SLABS * TC_TRACE_EVENTS + (ev)] = clock64();        \
+  } while (0)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap map_hi,
                     const __grid_constant__ CUtensorMap map_lo) {
@@ -201,6 +261,9 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   const pcodec_conv_desc &d = P.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = P.bn, stages = P.stages;
+  const bool trace = (P.raw_stages & 64) && blockIdx.x == ((P.raw_stages & 128) ? gridDim.x / 2 : 0) &&
+                     blockIdx.y == ((P.raw_stages & 128) ? gridDim.y - 1 : 0) && lane == 0;
+  if (threadIdx.x == 0) TC_TRACE_G(0);
   const bool split = P.split == 3;
   const int b_bytes = bn * 128;
   const int stage_bytes = TC_A_BYTES + (split ? 2 : 1) * b_bytes;  // raw A staging tile | B_hi | (B_lo)
@@ -210,27 +273,35 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   auto a_raw = [&](int s) { return smem_base + s * stage_bytes; };
   auto b_hi = [&](int s) { return smem_base + s * stage_bytes + TC_A_BYTES; };
   auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
-  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  // the stage area doubles as the epilogue's transpose scratch (2 KB per producer warp)
+  const uint32_t bar_base = smem_base + max(stages * stage_bytes, TC_PRODUCER_WARPS * 2048);
   auto raw_full = [&](int s) { return bar_base + 8u * s; };                   // cp.async landed        (128 loaders)
   auto raw_empty = [&](int s) { return bar_base + 8u * (stages + s); };       // staging tile consumed  (128 converters)
   auto full_b = [&](int s) { return bar_base + 8u * (2 * stages + s); };      // TMA bytes landed
-  auto empty_b = [&](int s) { return bar_base + 8u * (3 * stages + s); };     // MMAs that read B done  (tcgen05.commit)
+  // `empty_b(st)` = "slab in ring slot st consumed": ONE tcgen05.commit per slab releases both the B stage (to the
+  // TMA producer, a ring of `stages`) and the A operand buffer (to the converter group, which waits for the slot of
+  // slab s-2).  A commit costs the issuing thread ~150 clk, so one per slab instead of two matters.
+  auto empty_b = [&](int s) { return bar_base + 8u * (3 * stages + s); };     // MMAs of the slab in this slot done (tcgen05.commit)
   auto a_full = [&](int q) { return bar_base + 8u * (4 * stages + q); };      // A operand in TMEM      (128 converters)
   auto a_empty = [&](int q) { return bar_base + 8u * (4 * stages + 2 + q); }; // MMAs that read it done (tcgen05.commit)
   const uint32_t tmem_full = bar_base + 8u * (4 * stages + 4);
   const uint32_t tmem_slot = tmem_full + 8u;
   uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
 
-  // TMEM layout: [n_acc accumulators of bn columns][2 A-operand buffers of a_cols columns].
+  // TMEM layout: [n_acc accumulators of bn columns][a_ring A-operand buffers of a_cols columns].
   // Accumulators: the tensor core's fp32 accumulate truncates (round-toward-zero) once per MMA, so the error grows
   // linearly with the number of MMAs that touch an accumulator.  The small lo*hi / hi*lo products therefore get
   // their own accumulator (their truncation error is 2^-11 smaller in absolute terms), and the hi*hi products
   // round-robin over n_hi_acc accumulators; the epilogue sums them with round-to-nearest adds.
+  // A ring: refilling an A buffer after its MMAs retire takes ~800 clk (commit -> converter wake-up -> tcgen05.st ->
+  // wait::st -> arrive -> issuer wake-up) against 480..670 clk of MMA work per slab, so two buffers leave the tensor
+  // pipe idle half the time (measured with the clock64 timeline, tools/trace_tc.py); three hide the round trip.
   const int n_acc = P.n_hi_acc + (split ? 1 : 0);
   const int a_cols = split ? 64 : 32;            // hi (32 fp32 columns) + lo (32)
+  const int a_ring = P.a_ring;
   const uint32_t a_tmem_off = (uint32_t)(n_acc * bn);
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < n_acc * bn + 2 * a_cols) tmem_cols <<= 1;
+  while ((int)tmem_cols < n_acc * bn + a_ring * a_cols) tmem_cols <<= 1;
 
   __shared__ int s_dy[PCODEC_MAX_TAPS], s_dx[PCODEC_MAX_TAPS];
   __shared__ const float *s_seg_ptr[PCODEC_MAX_SEGMENTS];
@@ -248,15 +319,12 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 
   if (warp == TC_PRODUCER_WARPS + 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(raw_full(s), 128);
-      mbar_init(raw_empty(s), 128);
+      mbar_init(raw_full(s), 128); // cp.async completion arrives, one per loader thread
+      mbar_init(raw_empty(s), 4);  // one arrival per converter warp
       mbar_init(full_b(s), 1);
-      mbar_init(empty_b(s), 1);
+      mbar_init(empty_b(s), 1);  // one tcgen05.commit (by the issuer warp that owns the slab)
     }
-    for (int q = 0; q < 2; ++q) {
-      mbar_init(a_full(q), 128);
-      mbar_init(a_empty(q), 1);
-    }
+    for (int q = 0; q < 4; ++q) mbar_init(a_full(q), 4);  // a_full(0..3) (the a_empty slots are reused)
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
@@ -265,11 +333,30 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+  if (threadIdx.x == 0) TC_TRACE_G(1);
 
   const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
   const int n0 = blockIdx.y * bn;
   const int n_steps = P.n_steps;
 
+  if (warp < TC_PRODUCER_WARPS && (d.r1 || d.r2) && !(d.flags & PCODEC_FLAG_PIXEL_SHUFFLE2)) {
+    // The epilogue reads 128 x bn residual values that do not depend on the accumulators: pull them into L2 now so
+    // the epilogue's loads are L2 hits instead of a chain of serialised DRAM round trips (one CTA per SM: nothing
+    // else hides that latency).
+    const int prow = threadIdx.x & 127, psub = threadIdx.x >> 7;  // 3 threads per tile row
+    const int64_t pm = m0 + prow;
+    if (pm < P.M) {
+      const uint32_t pt = (uint32_t)pm / (uint32_t)d.grid_w;
+      const int pw = (int)((uint32_t)pm % (uint32_t)d.grid_w);
+      const int ph_ = (int)(pt % (uint32_t)d.grid_h);
+      const int64_t pn = (int64_t)(pt / (uint32_t)d.grid_h);
+      const int64_t ppix = (pn * d.out_h + (ph_ * d.out_step + d.out_off_y)) * (int64_t)d.out_w + (pw * d.out_step + d.out_off_x);
+      for (int c = psub * 32; c < bn && n0 + c < d.cout; c += 32 * (TC_PRODUCER_WARPS / 4)) {
+        if (d.r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r1 + ppix * d.r1_pixel_stride + n0 + c));
+        if (d.r2) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r2 + ppix * d.r2_pixel_stride + n0 + c));
+      }
+    }
+  }
   if (warp < TC_PRODUCER_WARPS) {
     // =============================== A producers ===============================
     if (warp < 4) {
@@ -286,11 +373,11 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         soff[i] = r * 128 + ((chunk ^ (r & 7)) << 4);
         const int64_t m = m0 + r;
         const bool okr = m < P.M;
-        const int64_t mm = okr ? m : 0;
-        const int w = (int)(mm % d.grid_w);
-        const int64_t t = mm / d.grid_w;
-        const int h = (int)(t % d.grid_h);
-        const int n = (int)(t / d.grid_h);
+        const uint32_t mm = okr ? (uint32_t)m : 0u;  // M < 2^31 (checked on the host): 32-bit divisions
+        const int w = (int)(mm % (uint32_t)d.grid_w);
+        const uint32_t t = mm / (uint32_t)d.grid_w;
+        const int h = (int)(t % (uint32_t)d.grid_h);
+        const int n = (int)(t / (uint32_t)d.grid_h);
         ih0[i] = okr ? h * d.in_step : -(1 << 28);
         iw0[i] = w * d.in_step;
         pix0[i] = (n * d.in_h + h * d.in_step) * d.in_w + w * d.in_step;
@@ -313,13 +400,16 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
           rowmask |= (v ? 1u : 0u) << i;
         }
         for (int kc = 0; kc < seg_slabs; ++kc, ++s) {
-          mbar_wait(raw_empty(st), eph);
+          mbar_wait_warp(raw_empty(st), eph, lane);
+          if (warp == 0) TC_TRACE(s, 0);
           const uint32_t dst = a_raw(st);
           const uint32_t mask = (kc * TC_BK + chunk * 4 < seg_channels) ? rowmask : 0u;
+          if (!(P.raw_stages & 1)) {
 #pragma unroll
-          for (int i = 0; i < RPT; ++i)
-            cp_async16(dst + soff[i], rowptr[i] + kc * TC_BK, ((mask >> i) & 1u) ? 16u : 0u);
-          cp_async_arrive_noinc(raw_full(st));
+            for (int i = 0; i < RPT; ++i)
+              cp_async16(dst + soff[i], rowptr[i] + kc * TC_BK, ((mask >> i) & 1u) ? 16u : 0u);
+          }
+          cp_async_arrive_noinc(raw_full(st));  // per-thread: fires when this thread's copies have landed
           if (++st == stages) { st = 0; eph ^= 1u; }
         }
         if (++tap == n_taps) { tap = 0; ++seg; }
@@ -332,24 +422,38 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
       const int arow = (warp & 3) * 32 + lane;
       const uint32_t row_off = arow * 128, row_x = (uint32_t)(arow & 7);
       const uint32_t lane_base = tmem_acc + a_tmem_off + ((uint32_t)((warp & 3) * 32) << 16);
-      int st = 0, q = 0;
-      uint32_t ph = 0, qph = 1;
-      for (int s = 0; s < n_steps; ++s) {
-        mbar_wait(raw_full(st), ph);
+      // Two converter groups (warps 4-7 / 8-11) take alternate K slabs, each with its own A operand buffer: one
+      // group's wait -> LDS -> tcgen05.st -> wait::st -> arrive chain (latency bound, ~1 us) overlaps the other's.
+      const int grp = (warp - 4) >> 2;
+      for (int s = grp; s < n_steps; s += 2) {
+        const int q = s % a_ring;
+        const int st = s % stages;
+        const uint32_t ph = (uint32_t)(s / stages) & 1u;
+        if ((warp & 3) == 0) TC_TRACE(s, 2);
+        {  // lane 0: A staging tile landed; lane 1: this slab's weights landed (so a_full tells the MMA warps both)
+          const uint32_t wbar = lane == 0 ? raw_full(st) : full_b(st);
+          if (lane < 2) mbar_wait(wbar, ph);
+          __syncwarp();
+        }
+        if ((warp & 3) == 0) TC_TRACE(s, 3);
         const uint8_t *src = smem_gen + (size_t)st * stage_bytes + row_off;
         float4 x[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4 *>(src + (((uint32_t)c ^ row_x) << 4));
-        mbar_arrive(raw_empty(st));  // staging tile consumed (values are in registers)
         if (square) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) { x[c].x *= x[c].x; x[c].y *= x[c].y; x[c].z *= x[c].z; x[c].w *= x[c].w; }
         }
-        mbar_wait(a_empty(q), qph);  // MMAs that read this A buffer two slabs ago have retired
+        if (s >= a_ring) {  // MMAs that read this A buffer a_ring slabs ago have retired
+          const int sp = s - a_ring;
+          mbar_wait_warp(empty_b(sp % stages), (uint32_t)(sp / stages) & 1u, lane);
+        }
+        if ((warp & 3) == 0) TC_TRACE(s, 4);
         tc_fence_after();
         const uint32_t ta = lane_base + (uint32_t)(q * a_cols);
-        tmem_st32(ta, x);
-        if (split) {
+        if (!(P.raw_stages & 4)) tmem_st32(ta, x);
+        mbar_arrive_warp(raw_empty(st), lane);  // staging tile consumed (the TMEM store has read the registers)
+        if (split && !(P.raw_stages & 4)) {
           float4 l[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -362,75 +466,127 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(a_full(q));
-        if (++st == stages) { st = 0; ph ^= 1u; }
-        q ^= 1;
-        if (q == 0) qph ^= 1u;
+        if ((warp & 3) == 0) TC_TRACE(s, 5);
+        mbar_arrive_warp(a_full(q), lane);
+        if ((warp & 3) == 0) TC_TRACE(s, 6);
       }
     }
 
     // =============================== epilogue ===============================
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 0) TC_TRACE_G(2);
     const int quarter = warp & 3;      // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    const int half = warp >> 2;        // warps w and w+4 share a quarter and interleave the 16-column groups
+    const int third = warp >> 2;       // warps w, w+4, w+8 share a quarter and interleave the 16-column groups
     const int row = quarter * 32 + lane;  // TMEM lane == tile row
     const int64_t m = m0 + row;
     const bool row_ok = m < P.M;
     const int64_t mm = row_ok ? m : 0;
-    const int w = (int)(mm % d.grid_w);
-    const int64_t t = mm / d.grid_w;
-    const int h = (int)(t % d.grid_h);
-    const int64_t n = t / d.grid_h;
+    const uint32_t mt = (uint32_t)mm / (uint32_t)d.grid_w;
+    const int w = (int)((uint32_t)mm % (uint32_t)d.grid_w);
+    const int h = (int)(mt % (uint32_t)d.grid_h);
+    const int64_t n = (int64_t)(mt / (uint32_t)d.grid_h);
     const int oh = h * d.out_step + d.out_off_y, ow = w * d.out_step + d.out_off_x;
     const int64_t opix = (n * d.out_h + oh) * (int64_t)d.out_w + ow;
     const bool shuffle = (d.flags & PCODEC_FLAG_PIXEL_SHUFFLE2) != 0;
     const bool has_r2 = d.r2 != nullptr;
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    for (int c0 = half * 16; c0 < bn; c0 += 32) {
-      float acc[16];
-      tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective: executed by all lanes, stores are predicated
-      for (int a = 1; a < n_acc; ++a) {
-        float part[16];
-        tmem_ld16(lane_addr + (uint32_t)(a * bn + c0), part);
+    // which accumulators were written (short reductions touch fewer than n_hi_acc hi accumulators)
+    uint32_t acc_mask = 0;
+    for (int j = 0; j < P.n_hi_acc; ++j)
+      if (n_steps > j) acc_mask |= 1u << j;
+    if (split) acc_mask |= 1u << P.n_hi_acc;
+    if (!shuffle) {
+      // Coalesced epilogue: a thread owns one tile ROW in tensor memory, but rows are `out_pixel_stride` floats
+      // apart in global memory, so a row-per-thread store touches 32 lines per instruction.  Each warp therefore
+      // transposes its 32 rows x 16 columns through a private 2 KB shared-memory tile (the pipeline stages are
+      // idle by now; 16-byte chunks XOR-swizzled so both phases are bank-conflict free) and then works with
+      // 4 lanes per row / 8 rows per instruction: residual loads and output stores are full 64-byte runs.
+      uint8_t *stg = smem_gen + warp * 2048;
+      const int rl = lane >> 2, cc = lane & 3;  // transposed phase: row (within a group of 8) and 16-byte chunk
+      int64_t opix_t[4];
+      uint32_t ok_t = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += part[j];
+      for (int i = 0; i < 4; ++i) {
+        const int src = i * 8 + rl;
+        const uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)opix, src);
+        const uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)((uint64_t)opix >> 32), src);
+        opix_t[i] = (int64_t)(((uint64_t)hi << 32) | lo);
+        ok_t |= (__shfl_sync(0xFFFFFFFFu, row_ok ? 1u : 0u, src) & 1u) << i;
       }
-      if (!row_ok) continue;
-      const int co0 = n0 + c0;
-      float bias[16];
+      const uint32_t wr_off = (uint32_t)lane * 64u, wr_x = (uint32_t)(lane >> 1) & 3u;
+      for (int c0 = third * 16; c0 < bn; c0 += 16 * (TC_PRODUCER_WARPS / 4)) {
+        if (n0 + c0 >= d.cout) break;  // padded last N tile
+        float acc[16];
+        tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective
+#pragma unroll 1
+        for (int a = 1; a < n_acc; ++a) {
+          if (!((acc_mask >> a) & 1u)) continue;
+          float part[16];
+          tmem_ld16(lane_addr + (uint32_t)(a * bn + c0), part);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) bias[j] = d.bias ? __ldg(d.bias + co0 + j) : 0.f;
-      if (!shuffle) {
-        float r1[16], r2[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 a = d.r1 ? *reinterpret_cast<const float4 *>(d.r1 + opix * d.r1_pixel_stride + co0 + 4 * q)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 b = d.r2 ? *reinterpret_cast<const float4 *>(d.r2 + opix * d.r2_pixel_stride + co0 + 4 * q)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          r1[4 * q] = a.x; r1[4 * q + 1] = a.y; r1[4 * q + 2] = a.z; r1[4 * q + 3] = a.w;
-          r2[4 * q] = b.x; r2[4 * q + 1] = b.y; r2[4 * q + 2] = b.z; r2[4 * q + 3] = b.w;
+          for (int j = 0; j < 16; ++j) acc[j] += part[j];
         }
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = tc_epilogue(d.epilogue, acc[j] + bias[j], r1[j], r2[j], has_r2);
-        float *dst = d.out + opix * d.out_pixel_stride + co0;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-      } else {
+          *reinterpret_cast<float4 *>(stg + wr_off + (((uint32_t)q ^ wr_x) << 4)) =
+              make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        __syncwarp();
+        const int co = n0 + c0 + 4 * cc;
+        const float4 bias4 = d.bias ? __ldg(reinterpret_cast<const float4 *>(d.bias + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + rl;
+          const float4 v = *reinterpret_cast<const float4 *>(stg + r * 64 + (((uint32_t)cc ^ ((uint32_t)(r >> 1) & 3u)) << 4));
+          if (!((ok_t >> i) & 1u)) continue;
+          const float4 a1 = d.r1 ? __ldg(reinterpret_cast<const float4 *>(d.r1 + opix_t[i] * d.r1_pixel_stride + co))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 a2 = d.r2 ? __ldg(reinterpret_cast<const float4 *>(d.r2 + opix_t[i] * d.r2_pixel_stride + co))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 o = tc_epilogue4(d.epilogue, make_float4(v.x + bias4.x, v.y + bias4.y, v.z + bias4.z, v.w + bias4.w),
+                                        a1, a2, has_r2);
+          *reinterpret_cast<float4 *>(d.out + opix_t[i] * d.out_pixel_stride + co) = o;
+        }
+        __syncwarp();
+      }
+    } else {
+      for (int c0 = third * 16; c0 < bn; c0 += 16 * (TC_PRODUCER_WARPS / 4)) {
+        if (n0 + c0 >= d.cout) break;  // padded last N tile
+        float acc[16];
+        tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective: executed by all lanes, stores are predicated
+        for (int a = 1; a < n_acc; ++a) {
+          if (!((acc_mask >> a) & 1u)) continue;
+          float part[16];
+          tmem_ld16(lane_addr + (uint32_t)(a * bn + c0), part);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = co0 + j;
-          const float v = tc_epilogue(d.epilogue, acc[j] + bias[j], 0.f, 0.f, false);
-          const int c = co >> 2, si = (co >> 1) & 1, sj = co & 1;
-          const int64_t sp = (n * d.out_h + (2 * oh + si)) * (int64_t)d.out_w + (2 * ow + sj);
-          d.out[sp * d.out_pixel_stride + c] = v;
+          for (int j = 0; j < 16; ++j) acc[j] += part[j];
+        }
+        if (!row_ok) continue;
+        const int co0 = n0 + c0;
+#pragma unroll 1
+        for (int j4 = 0; j4 < 4; ++j4) {  // 4 consecutive conv channels = the 2x2 sub-pixels of one output channel
+          const int co = co0 + 4 * j4;
+          const float4 b4 = d.bias ? __ldg(reinterpret_cast<const float4 *>(d.bias + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float a4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a4[e] = acc[0];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj)  // static register indexing
+            if ((jj >> 2) == j4) a4[jj & 3] = acc[jj];
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 o = tc_epilogue4(d.epilogue, make_float4(a4[0] + b4.x, a4[1] + b4.y, a4[2] + b4.z, a4[3] + b4.w), z, z, false);
+          const int c = co >> 2;
+          const int64_t sp0 = (n * d.out_h + 2 * oh) * (int64_t)d.out_w + 2 * ow;
+          float *o0 = d.out + sp0 * d.out_pixel_stride + c;
+          o0[0] = o.x;
+          o0[d.out_pixel_stride] = o.y;
+          o0[(int64_t)d.out_w * d.out_pixel_stride] = o.z;
+          o0[((int64_t)d.out_w + 1) * d.out_pixel_stride] = o.w;
         }
       }
     }
     tc_fence_before();
+    if (threadIdx.x == 0) TC_TRACE_G(3);
   } else if (warp == TC_PRODUCER_WARPS) {
     // =============================== TMA producer for B ===============================
     if (lane == 0) {
@@ -441,9 +597,13 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         if (st == stages) { st = 0; ph ^= 1u; }
         mbar_wait(empty_b(st), ph);
         const int k = tap * d.cin_total + seg_cbase + kc * TC_BK;
-        mbar_expect_tx(full_b(st), (uint32_t)((split ? 2 : 1) * b_bytes));
-        tma_load_2d(b_hi(st), &map_hi, full_b(st), k, n0);
-        if (split) tma_load_2d(b_lo(st), &map_lo, full_b(st), k, n0);
+        if (P.raw_stages & 2) {
+          mbar_arrive(full_b(st));
+        } else {
+          mbar_expect_tx(full_b(st), (uint32_t)((split ? 2 : 1) * b_bytes));
+          tma_load_2d(b_hi(st), &map_hi, full_b(st), k, n0);
+          if (split) tma_load_2d(b_lo(st), &map_lo, full_b(st), k, n0);
+        }
         const int sc = d.seg[seg].channels;
         if (++kc == (sc + TC_BK - 1) / TC_BK) {
           kc = 0;
@@ -453,39 +613,51 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     }
   } else {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow) and one lane chosen with elect.sync issues: with
+    // `if (lane == 0)` ptxas wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop (~55 clk per instruction, which made
+    // the issuing thread the bottleneck); elected in a converged warp the 12 MMAs of a slab issue straight-line at
+    // the tensor pipe's own rate (N/2 clk each — tools/ubench/mma_rate.cu).
+    {
       // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int st = 0, hi_idx = 0, q = 0;
-      uint32_t ph = 0, qph = 0;
       const uint32_t acc_lo = tmem_acc + (uint32_t)(P.n_hi_acc * bn);
-      for (int s = 0; s < n_steps; ++s) {
-        mbar_wait(a_full(q), qph);
-        mbar_wait(full_b(st), ph);
-        tc_fence_after();
-        const uint64_t db_hi = umma_desc_sw128(b_hi(st)), db_lo = umma_desc_sw128(b_lo(st));
-        const uint32_t ta_hi = tmem_acc + a_tmem_off + (uint32_t)(q * a_cols);
-        const uint32_t ta_lo = ta_hi + 32u;
-        const uint32_t acc_hi = tmem_acc + (uint32_t)(hi_idx * bn);
-        const bool first_hi = s < P.n_hi_acc;  // first slab that touches this hi accumulator
+      int st = 0, hi_idx = 0, q = 0;
+      uint32_t qph = 0;
+      // tcgen05.commit returns only when the queued MMAs have (nearly) retired, so every cycle between a commit and
+      // the next slab's first MMA is tensor-pipe idle time: the whole loop therefore runs in ONE elected thread (no
+      // per-slab __syncwarp / re-election; a poll of an already-completed mbarrier by the issuing thread itself costs
+      // ~15 clk against ~135 clk for lane-0-polls-then-syncwarp).
+      if (elect_one()) {
+        for (int s = 0; s < n_steps; ++s) {
+          TC_TRACE(s, 7);
+          mbar_wait(a_full(q), qph);  // A operand in TMEM and (checked by the converters) B in shared memory
+          TC_TRACE(s, 8);
+          tc_fence_after();
+          const uint64_t db_hi = umma_desc_sw128(b_hi(st)), db_lo = umma_desc_sw128(b_lo(st));
+          const uint32_t ta_hi = tmem_acc + a_tmem_off + (uint32_t)(q * a_cols);
+          const uint32_t ta_lo = ta_hi + 32u;
+          const uint32_t acc_hi = tmem_acc + (uint32_t)(hi_idx * bn);
+          const bool first_hi = s < P.n_hi_acc;  // first slab that touches this hi accumulator
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t adv = (uint64_t)(k * 2);  // B: 8 tf32 = 32 bytes = 2 x 16-byte units inside the swizzle row
-          const uint32_t ak = (uint32_t)(k * 8);   // A: 8 fp32 columns of tensor memory
-          umma_tf32_ts(acc_hi, ta_hi + ak, db_hi + adv, idesc, (!first_hi || k > 0) ? 1u : 0u);
-          if (split) {
-            umma_tf32_ts(acc_lo, ta_lo + ak, db_hi + adv, idesc, (s > 0 || k > 0) ? 1u : 0u);
-            umma_tf32_ts(acc_lo, ta_hi + ak, db_lo + adv, idesc, 1u);
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);  // B: 8 tf32 = 32 bytes = 2 x 16-byte units inside the swizzle row
+            const uint32_t ak = (uint32_t)(k * 8);   // A: 8 fp32 columns of tensor memory
+            umma_tf32_ts(acc_hi, ta_hi + ak, db_hi + adv, idesc, (!first_hi || k > 0) ? 1u : 0u);
+            if (split) {
+              umma_tf32_ts(acc_lo, ta_lo + ak, db_hi + adv, idesc, (s > 0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(acc_lo, ta_hi + ak, db_lo + adv, idesc, 1u);
+            }
           }
+          TC_TRACE(s, 11);
+          umma_commit(empty_b(st));  // B slot + A operand buffer reusable once these MMAs retire
+          TC_TRACE(s, 10);
+          if (++st == stages) st = 0;
+          if (++hi_idx == P.n_hi_acc) hi_idx = 0;
+          if (++q == a_ring) { q = 0; qph ^= 1u; }
         }
-        umma_commit(empty_b(st));  // B slot reusable once these MMAs retire (implies tcgen05.fence::before_thread_sync)
-        umma_commit(a_empty(q));   // A operand buffer reusable
-        if (++st == stages) { st = 0; ph ^= 1u; }
-        if (++hi_idx == P.n_hi_acc) hi_idx = 0;
-        q ^= 1;
-        if (q == 0) qph ^= 1u;
+        umma_commit(tmem_full);
       }
-      umma_commit(tmem_full);
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -493,6 +665,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_acc, tmem_cols);
   }
+  if (threadIdx.x == 0) TC_TRACE_G(4);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -532,23 +705,24 @@ __global__ void split_weights_kernel(const float *__restrict__ w_tap_major, int 
   lo[i] = w - h;
 }
 
-// N tile: the widest multiple of 16 that divides cout and fits the TMEM budget.  Long reductions (K >= 1024) get
-// a narrower tile (<= 128 columns) so that 3 hi accumulators + 1 lo accumulator fit in the 512 TMEM columns: the
-// tensor core truncates once per MMA per accumulator, so spreading the K slabs over more accumulators keeps the
-// result at fp32-class accuracy (measured: rms 1e-5 -> 3e-6 at K = 4800).
-int pick_bn(int cout, int k_total) {
+// N tile: at most 128 columns, a multiple of 16, so that at least two hi accumulators + the lo accumulator + a
+// 2-deep A operand ring fit the 512 TMEM columns (3 x 128 + 128).  Tiles need not divide cout: the last tile may be
+// padded (TMA zero-fills out-of-range weight rows, the epilogue skips columns >= cout); pick the tiling with the
+// least padding, then the fewest tiles.
+int pick_bn(int cout, int /*k_total*/) {
   if (cout % 16 != 0) return 0;
-  int cap = k_total >= 1024 ? 128 : 192;  // 2 accumulators x 192 + 128 A-operand columns = 512 TMEM columns
+  int cap = 128;
   if (const char *e = getenv("PCODEC_TC_BNCAP")) cap = atoi(e);  // experiment knob
-  int fallback = 0;
-  for (int tiles = 1; tiles <= 16; ++tiles) {
-    if (cout % tiles) continue;
-    const int bn = cout / tiles;
-    if (bn % 16 != 0) continue;
-    if (bn <= 256 && fallback == 0) fallback = bn;
-    if (bn <= cap) return (fallback != 0 && tiles > 2 * (cout / fallback)) ? fallback : bn;
+  int best = 0, best_waste = 1 << 30;
+  const int t0 = (cout + cap - 1) / cap;
+  for (int tiles = t0; tiles <= t0 + 3; ++tiles) {
+    int bn = (cout + tiles - 1) / tiles;
+    bn = (bn + 15) & ~15;
+    if (bn > cap || bn < 16) continue;
+    const int waste = tiles * bn - cout;
+    if (waste < best_waste) { best_waste = waste; best = bn; }
   }
-  return fallback;
+  return best;
 }
 
 }  // namespace
@@ -565,7 +739,7 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
   h->cout = cout;
   h->k_total = n_taps * cin_total;
   h->bn = bn;
-  h->n_tiles = cout / bn;
+  h->n_tiles = (cout + bn - 1) / bn;
   const size_t bytes = sizeof(float) * (size_t)cout * h->k_total;
   if (cudaMalloc(&h->dev_hi, bytes) != cudaSuccess || cudaMalloc(&h->dev_lo, bytes) != cudaSuccess) {
     delete h;
@@ -597,6 +771,12 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
   return PCODEC_OK;
 }
 
+extern "C" int pcodec_debug_tc_trace(long long *out, int n) {
+  const int total = TC_TRACE_SLABS * TC_TRACE_EVENTS + 32;
+  if (!out || n < total) return total;
+  return cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * total) == cudaSuccess ? total : -1;
+}
+
 extern "C" void pcodec_conv_tc_release(void *handle) {
   if (!handle) return;
   TcWeights *h = static_cast<TcWeights *>(handle);
@@ -622,6 +802,7 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   TcParams P;
   P.d = *desc;
   P.M = (int64_t)desc->batch * desc->grid_h * desc->grid_w;
+  if (P.M >= (1ll << 31) - TC_BM) return PCODEC_ERR_UNSUPPORTED;  // 32-bit pixel arithmetic in the kernel
   P.bn = h->bn;
   P.split = desc->tc_split;
   int n_steps = 0;
@@ -629,7 +810,7 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   P.n_steps = n_steps;
   const bool split3 = P.split == 3;
   const int stage_bytes = TC_A_BYTES + (split3 ? 2 : 1) * h->bn * 128;  // raw A staging tile | B_hi | (B_lo)
-  auto need = [&](int st) { return st * stage_bytes + 1024 + 8 * (4 * st + 6) + 64; };
+  auto need = [&](int st) { return std::max(st * stage_bytes, TC_PRODUCER_WARPS * 2048) + 1024 + 8 * (4 * st + 6) + 64; };
   int stages = 2;
   while (need(stages + 1) <= TC_SMEM_LIMIT && stages < 8) ++stages;
   if (const char *e = getenv("PCODEC_TC_STAGES")) stages = std::min(stages, atoi(e));  // experiment knob
@@ -637,17 +818,33 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   if (stages < 1 || need(stages) > TC_SMEM_LIMIT) return PCODEC_ERR_UNSUPPORTED;
   P.stages = stages;
   P.raw_stages = 0;
+  if (const char *e = getenv("PCODEC_TC_DEBUG")) P.raw_stages = atoi(e);  // experiment knob (wrong results!)
   {
-    // TMEM columns: n_acc accumulators of bn + two A operand buffers (hi 32 [+ lo 32] columns each)
+    // TMEM columns: (n_hi hi accumulators + 1 lo) of bn columns + a_ring A operand buffers (hi 32 [+ lo 32] columns).
+    // Prefer a 3-deep A ring; spend what is left on hi accumulators (up to 4).
     const int a_cols = split3 ? 64 : 32;
-    int n_acc = (512 - 2 * a_cols) / h->bn;
+    int ring = 3;
+    int n_acc = (512 - ring * a_cols) / h->bn;
+    if (n_acc - (split3 ? 1 : 0) < 2) {  // wide tile: fall back to a 2-deep ring rather than a single hi accumulator
+      ring = 2;
+      n_acc = (512 - ring * a_cols) / h->bn;
+    }
+    if (const char *e = getenv("PCODEC_TC_RING")) {  // experiment knob
+      ring = std::max(2, std::min(4, atoi(e)));
+      n_acc = (512 - ring * a_cols) / h->bn;
+    }
     int n_hi = n_acc - (split3 ? 1 : 0);
     if (n_hi > 4) n_hi = 4;
-    if (n_hi > n_steps) n_hi = n_steps;
     if (n_hi < 1) return PCODEC_ERR_UNSUPPORTED;
+    if (ring > stages) ring = stages;  // the "consumed" barrier of slab s - ring must not have been recycled
+    if (ring < 1) ring = 1;
+    P.a_ring = ring;
     P.n_hi_acc = n_hi;
   }
   const int smem = need(stages);
+  if (getenv("PCODEC_TC_VERBOSE"))
+    fprintf(stderr, "[conv_tc] M=%lld bn=%d n_tiles=%d n_steps=%d stages=%d n_hi=%d ring=%d split=%d smem=%d\n", (long long)P.M,
+            h->bn, h->n_tiles, n_steps, stages, P.n_hi_acc, P.a_ring, P.split, smem);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
