@@ -159,11 +159,13 @@ def conv_roofline(net, peaks, peak_kind):
 
     P = net.prepare()
     E = P["eng"]
+    E.begin(0)  # latch the CURRENT stream for this thread's launches (the CUDA events below are recorded on it)
     pc = P["g_a"][0]["c2"]
-    x = Act(torch.randn(1, 256, 384, 192, device=E.device))
-    out = new_act(1, 128, 192, 192, E.device)
+    nb = 8  # images per launch: 3072 CTAs = 20.8 waves of 148, as in the batched run (one image is 2.6 waves)
+    x = Act(torch.randn(nb, 256, 384, 192, device=E.device))
+    out = new_act(nb, 128, 192, 192, E.device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=E.device)
-    flops = 2.0 * 128 * 192 * 192 * (25 * 192)
+    flops = 2.0 * nb * 128 * 192 * 192 * (25 * 192)
     for _ in range(3):
         E.conv(pc, [x], out)
     times = []
@@ -178,12 +180,18 @@ def conv_roofline(net, peaks, peak_kind):
     avg = sum(times) / len(times)
     achieved = flops / avg / 1e12
     peak = peaks["bf16_tflops"]
-    # DRAM traffic of this exact launch from the committed `ncu --set full` capture
-    # (profiles/r01_ncu_full_conv_taps_tc_5x5s2_192.csv: dram__bytes_read 114.85 MB + dram__bytes_write 12.69 MB);
-    # algorithmic bytes = 75.5 MB input + 7.4 MB TF32 hi/lo weights + 18.9 MB output = 101.8 MB.
-    return {"bound": "tensor", "kernel": "conv_taps_tc_kernel (tcgen05 3xTF32; 5x5 s2 192->192 @128x192 out)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 127.54e6,
-            "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes": 101.8e6,
+    # DRAM traffic of this exact launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set
+    # full` capture of tools/prof_conv_one.py, recorded in profiles/roofline_traffic.json; null if not captured.
+    # Algorithmic bytes = NHWC input + TF32 hi/lo weights + output.
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.isfile(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    alg_bytes = 4.0 * (nb * 256 * 384 * 192 + 2 * 25 * 192 * 192 + nb * 128 * 192 * 192)
+    return {"bound": "tensor", "kernel": f"conv_taps_tc_kernel (tcgen05 3xTF32; 5x5 s2 192->192, {nb} x 256x384 -> 128x192)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes": alg_bytes,
             "peak_kind": peak_kind + " bf16 burst (cuBLAS); this kernel issues 3 TF32 MMAs per algorithmic MAC, "
                          "TF32 runs at half the bf16 rate, so frac <= 1/6",
             "tensor_pipe_frac_of_tf32_peak": 3.0 * achieved / (peak / 2.0),
@@ -213,27 +221,49 @@ def run_ours(args):
     B = args.batch
     x_host = torch.cat([synthetic_image((1, 3, H, W), seed=rank * 1000 + i) for i in range(B)]).pin_memory()
     x_dev = x_host.to(dev)
+    xhat_host = torch.empty_like(x_host).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    from progressivecodec_b200 import pipeline
+
     def step_device():
-        for q in QUALITIES:
-            c = net.compress(x_dev, quality=q, return_device_streams=True)
-            net.decompress(c, c["shape"], quality=q)
+        if args.no_pipeline:
+            for q in QUALITIES:
+                c = net.compress(x_dev, quality=q, return_device_streams=True)
+                net.decompress(c, c["shape"], quality=q)
+        else:  # same calls, compress(q+1) overlapped with decompress(q) on two streams / host threads
+            pipeline.sweep(net, x_dev, QUALITIES, keep=False)
 
     h2d = [0]
     d2h = [0]
 
     def step_e2e():
         h2d[0] = d2h[0] = 0
-        for q in QUALITIES:
-            xd = x_host.to(dev, non_blocking=True)
-            h2d[0] += x_host.numel() * 4
-            c = net.compress(xd, quality=q)
+        if args.no_pipeline:
+            for q in QUALITIES:
+                xd = x_host.to(dev, non_blocking=True)
+                h2d[0] += x_host.numel() * 4
+                c = net.compress(xd, quality=q)
+                nbytes = sum(len(s) for sl in c["strings"][0] for s in sl) + sum(len(s) for s in c["strings"][1])
+                d2h[0] += nbytes
+                r = net.decompress(c["strings"], c["shape"], quality=q)["x_hat"]
+                xhat_host.copy_(r, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                h2d[0] += nbytes
+                d2h[0] += r.numel() * 4
+            return
+        # host image in (pinned -> device), python `bytes` strings between the stages, x_hat copied back to the host
+        xd = x_host.to(dev, non_blocking=True)
+        h2d[0] += x_host.numel() * 4
+
+        def on_result(q, c, r):
             nbytes = sum(len(s) for sl in c["strings"][0] for s in sl) + sum(len(s) for s in c["strings"][1])
-            d2h[0] += nbytes
-            r = net.decompress(c["strings"], c["shape"], quality=q)["x_hat"].cpu()
+            d2h[0] += nbytes + r["x_hat"].numel() * 4
             h2d[0] += nbytes
-            d2h[0] += r.numel() * 4
+            xhat_host.copy_(r["x_hat"], non_blocking=True)  # pinned destination
+            torch.cuda.current_stream().synchronize()
+
+        pipeline.sweep(net, xd, QUALITIES, host_strings=True, on_result=on_result, keep=False)
 
     def barrier():
         if world > 1:
@@ -310,6 +340,8 @@ def run_ours(args):
                            "model": "ChannelProgresssiveWACNN authors' flags (mdmh-mem5-de), synthetic calibrated weights",
                            "batch_per_gpu": B, "qualities": QUALITIES,
                            "l2": "256 MiB buffer written between steps; working set (0.6 GB weights + activations) >> 126 MB L2",
+                           "pipeline": ("none" if args.no_pipeline else
+                                        "compress(q+1) overlaps decompress(q): 2 host threads / CUDA streams (pipeline.sweep)"),
                            "parallelism": f"dp{world} (images sharded, no collective in the timed region)"},
                 "e2e": {"value": e2e_value, "unit": "image-qualities/s", "h2d_bytes_per_step": h2d[0],
                         "d2h_bytes_per_step": d2h[0], "steps": e2e_steps},
@@ -328,6 +360,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="768x512 images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="compress/decompress strictly back to back")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -705,24 +705,26 @@ __global__ void split_weights_kernel(const float *__restrict__ w_tap_major, int 
   lo[i] = w - h;
 }
 
-// N tile: at most 128 columns, a multiple of 16, so that at least two hi accumulators + the lo accumulator + a
-// 2-deep A operand ring fit the 512 TMEM columns (3 x 128 + 128).  Tiles need not divide cout: the last tile may be
-// padded (TMA zero-fills out-of-range weight rows, the epilogue skips columns >= cout); pick the tiling with the
-// least padding, then the fewest tiles.
-int pick_bn(int cout, int /*k_total*/) {
+// N tile: the fewest tiles (least A-operand re-reading, fewest CTAs) such that the accumulators fit tensor memory
+// next to a 2-deep A operand ring AND no hi accumulator sees more than ~320 MMAs: the tensor core truncates once per
+// MMA per accumulator, so spreading a long reduction over several accumulators keeps the result at fp32-class
+// accuracy (measured: rms 3e-5 -> 3e-6 at K = 4800 going from 1 to 4 accumulators).  Tiles are multiples of 16 and
+// need not divide cout: the last tile may be padded (TMA zero-fills out-of-range weight rows, the epilogue skips
+// columns >= cout).
+int pick_bn(int cout, int k_total) {
   if (cout % 16 != 0) return 0;
-  int cap = 128;
+  int cap = 256;
   if (const char *e = getenv("PCODEC_TC_BNCAP")) cap = atoi(e);  // experiment knob
-  int best = 0, best_waste = 1 << 30;
-  const int t0 = (cout + cap - 1) / cap;
-  for (int tiles = t0; tiles <= t0 + 3; ++tiles) {
+  const int n_steps = (k_total + TC_BK - 1) / TC_BK;
+  const int need_hi = std::max(1, (4 * n_steps + 319) / 320);
+  for (int tiles = 1; tiles <= 64; ++tiles) {
     int bn = (cout + tiles - 1) / tiles;
     bn = (bn + 15) & ~15;
-    if (bn > cap || bn < 16) continue;
-    const int waste = tiles * bn - cout;
-    if (waste < best_waste) { best_waste = waste; best = bn; }
+    if (bn > cap) continue;
+    const int n_acc = (512 - 128) / bn;  // next to two 64-column A operand buffers
+    if (n_acc - 1 >= std::min(need_hi, 4) || bn == 16) return bn;
   }
-  return best;
+  return 0;
 }
 
 }  // namespace
@@ -823,9 +825,10 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
     // TMEM columns: (n_hi hi accumulators + 1 lo) of bn columns + a_ring A operand buffers (hi 32 [+ lo 32] columns).
     // Prefer a 3-deep A ring; spend what is left on hi accumulators (up to 4).
     const int a_cols = split3 ? 64 : 32;
+    const int need_hi = std::min(4, std::max(1, (4 * n_steps + 319) / 320));  // same rule as pick_bn
     int ring = 3;
     int n_acc = (512 - ring * a_cols) / h->bn;
-    if (n_acc - (split3 ? 1 : 0) < 2) {  // wide tile: fall back to a 2-deep ring rather than a single hi accumulator
+    if (n_acc - (split3 ? 1 : 0) < need_hi) {  // wide tile: a 2-deep ring rather than too few hi accumulators
       ring = 2;
       n_acc = (512 - ring * a_cols) / h->bn;
     }

@@ -719,15 +719,18 @@ class ChannelProgresssiveWACNN(nn.Module):
         groups = self.decode_groups if self.decode_groups else max(1, min(4, B // 4))
         groups = max(1, min(groups, B))
         if groups == 1:
+            # slot 1, not 0: slot 0 belongs to the encoder-side entry points, which pipeline.sweep() runs concurrently
             return {"x_hat": self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, 0, B, shape, quality,
-                                                    mask_pol)}
+                                                    mask_pol, slot=1)}
         import threading
 
         from .sharding import shard_bounds
 
         cur = torch.cuda.current_stream(dev)
         if self._streams is None or len(self._streams) < groups:
-            self._streams = [torch.cuda.Stream(device=dev) for _ in range(groups)]
+            # high priority: a group's entropy-decode launch is a handful of CTAs on its critical path; it should get
+            # the next free SM ahead of the wide convolution grids of other groups / of a concurrent compress()
+            self._streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(groups)]
         outs: List[Optional[Tensor]] = [None] * groups
         errs: List[Optional[BaseException]] = [None] * groups
 
