@@ -169,6 +169,10 @@ int pcodec_bottleneck_likelihood(const float *z_hat, int z_ps, const float *para
 #define PCODEC_FLAG_SQUARE_INPUT 1   /* A = x*x (GDN) */
 #define PCODEC_FLAG_PIXEL_SHUFFLE2 2 /* output channel co -> pixel (2h + (co>>1&1), 2w + (co&1)), channel co>>2; applied
                                         after the epilogue (subpel_conv3x3, layers.py:20-24) */
+#define PCODEC_FLAG_SUBPIXEL_NCHW 4  /* the 4 sub-pixel phases of a stride-2 transposed convolution computed as ONE
+                                        3x3-neighbourhood GEMM: conv channel co = (2*py + px) * C + c is stored to the
+                                        NCHW image out[n][c][2h+py][2w+px], C = out_channels (cout >= 4*C, tcgen05 path
+                                        only).  Used for the image layer of g_s (deconv(N, 3), CHProg_cnn.py:148-161) */
 
 typedef struct {
   const float *ptr; /* NHWC base of this channel segment */

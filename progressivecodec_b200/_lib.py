@@ -19,7 +19,7 @@ OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_OVERFLOW = 0, 1, 2, 3
 MASK_ONES, MASK_ZEROS, MASK_THRESHOLD = 0, 1, 2
 
 EPI_LINEAR, EPI_GELU, EPI_ADD, EPI_ADD_GELU, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP, EPI_CLAMP01 = range(9)
-FLAG_SQUARE_INPUT, FLAG_PIXEL_SHUFFLE2 = 1, 2
+FLAG_SQUARE_INPUT, FLAG_PIXEL_SHUFFLE2, FLAG_SUBPIXEL_NCHW = 1, 2, 4
 
 
 class Segment(C.Structure):

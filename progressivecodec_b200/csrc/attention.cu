@@ -82,6 +82,106 @@ window_attention_kernel(const float *__restrict__ qkv, int qkv_ps, float *__rest
   }
 }
 
+// Register-tiled variant for the head sizes the model uses (HD = 24 / 40 / 80): the thread's own q row lives in
+// registers (loaded straight from global memory, 16 bytes at a time), K and V rows are read from shared memory as
+// broadcast float4 (one LDS.128 feeds four FMAs — the scalar version above issues one LDS per FMA and is bound by the
+// shared-memory pipe), and the output row is written with 16-byte stores.  The accumulation order of every dot
+// product is unchanged, so results are bit-identical to the scalar kernel.
+template <int T, int HD>
+__global__ void __launch_bounds__(T)
+window_attention_v4_kernel(const float *__restrict__ qkv, int qkv_ps, float *__restrict__ out, int out_ps,
+                           const float *__restrict__ rel_bias, int H, int W, int C, int heads, int ws, int shift) {
+  __shared__ __align__(16) float sk[T * HD];
+  __shared__ __align__(16) float sv[T * HD];
+  __shared__ int s_region[T];
+  const int nww = W / ws, nwh = H / ws;
+  const int win = blockIdx.x % (nwh * nww);
+  const int b = blockIdx.x / (nwh * nww);
+  const int head = blockIdx.y;
+  const int wi = win / nww, wj = win % nww;
+  const int i = threadIdx.x;
+  const int hs = wi * ws + i / ws, wsft = wj * ws + i % ws;
+  const int ph = (hs + shift) % H, pw = (wsft + shift) % W;
+  const int64_t pix = ((int64_t)b * H + ph) * W + pw;
+  const float scale = rsqrtf((float)HD);
+  float q[HD];
+  {
+    const float *src = qkv + pix * qkv_ps + head * HD;
+#pragma unroll
+    for (int c = 0; c < HD / 4; ++c) {
+      const float4 a = *reinterpret_cast<const float4 *>(src + 4 * c);
+      const float4 k4 = *reinterpret_cast<const float4 *>(src + C + 4 * c);
+      const float4 v4 = *reinterpret_cast<const float4 *>(src + 2 * C + 4 * c);
+      q[4 * c] = __fmul_rn(a.x, scale); q[4 * c + 1] = __fmul_rn(a.y, scale);
+      q[4 * c + 2] = __fmul_rn(a.z, scale); q[4 * c + 3] = __fmul_rn(a.w, scale);
+      *reinterpret_cast<float4 *>(sk + i * HD + 4 * c) = k4;
+      *reinterpret_cast<float4 *>(sv + i * HD + 4 * c) = v4;
+    }
+    int region = 0;
+    if (shift > 0) {
+      const int rh = hs < H - ws ? 0 : (hs < H - shift ? 1 : 2);
+      const int rw = wsft < W - ws ? 0 : (wsft < W - shift ? 1 : 2);
+      region = rh * 3 + rw;
+    }
+    s_region[i] = region;
+  }
+  __syncthreads();
+  float s[T];
+  const float *bias = rel_bias + ((int64_t)head * T + i) * T;
+  const int my_region = s_region[i];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD / 4; ++c) {
+      const float4 k4 = *reinterpret_cast<const float4 *>(sk + j * HD + 4 * c);  // broadcast read
+      acc = fmaf(q[4 * c], k4.x, acc);
+      acc = fmaf(q[4 * c + 1], k4.y, acc);
+      acc = fmaf(q[4 * c + 2], k4.z, acc);
+      acc = fmaf(q[4 * c + 3], k4.w, acc);
+    }
+    float v = acc + __ldg(bias + j);
+    if (shift > 0 && s_region[j] != my_region) v += -100.0f;
+    s[j] = v;
+    mx = fmaxf(mx, v);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    s[j] = expf(s[j] - mx);
+    sum += s[j];
+  }
+  const float inv = 1.0f / sum;
+  float o[HD];
+#pragma unroll
+  for (int c = 0; c < HD; ++c) o[c] = 0.f;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    const float p = s[j] * inv;
+#pragma unroll
+    for (int c = 0; c < HD / 4; ++c) {
+      const float4 v4 = *reinterpret_cast<const float4 *>(sv + j * HD + 4 * c);
+      o[4 * c] = fmaf(p, v4.x, o[4 * c]);
+      o[4 * c + 1] = fmaf(p, v4.y, o[4 * c + 1]);
+      o[4 * c + 2] = fmaf(p, v4.z, o[4 * c + 2]);
+      o[4 * c + 3] = fmaf(p, v4.w, o[4 * c + 3]);
+    }
+  }
+  float *dst = out + pix * out_ps + head * HD;
+#pragma unroll
+  for (int c = 0; c < HD / 4; ++c)
+    *reinterpret_cast<float4 *>(dst + 4 * c) = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+}
+
+template <int T, int HD>
+int launch_attention_v4(const float *qkv, int qkv_ps, float *out, int out_ps, const float *rel_bias, int height, int width,
+                        int channels, int heads, int window, int shift, dim3 grid, cudaStream_t st) {
+  window_attention_v4_kernel<T, HD><<<grid, T, 0, st>>>(qkv, qkv_ps, out, out_ps, rel_bias, height, width, channels, heads,
+                                                         window, shift);
+  PCODEC_RETURN_LAUNCH();
+}
+
 __global__ void im2col_nchw_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int H, int W, int k,
                                    int stride, int pad, int OH, int OW, int k_pad, int64_t total) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,6 +213,15 @@ extern "C" int pcodec_window_attention(const float *qkv, int qkv_ps, float *out,
   const size_t smem = sizeof(float) * ((size_t)2 * T * (hd + 1) + (size_t)T * hd);
   dim3 grid((unsigned)(batch * (height / window) * (width / window)), (unsigned)heads);
   cudaStream_t st = as_stream(stream);
+  // 16-byte accesses need 16-byte aligned rows
+  const bool vec_ok = (qkv_ps % 4 == 0) && (out_ps % 4 == 0) && (channels % 4 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec_ok && T == 64 && hd == 24)
+    return launch_attention_v4<64, 24>(qkv, qkv_ps, out, out_ps, rel_bias, height, width, channels, heads, window, shift, grid, st);
+  if (vec_ok && T == 16 && hd == 40)
+    return launch_attention_v4<16, 40>(qkv, qkv_ps, out, out_ps, rel_bias, height, width, channels, heads, window, shift, grid, st);
+  if (vec_ok && T == 16 && hd == 80)
+    return launch_attention_v4<16, 80>(qkv, qkv_ps, out, out_ps, rel_bias, height, width, channels, heads, window, shift, grid, st);
   if (T == 64) {
     if (smem > 48 * 1024)
       PCODEC_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,

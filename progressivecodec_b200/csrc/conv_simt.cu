@@ -278,6 +278,8 @@ static int validate(const pcodec_conv_desc *d) {
   if (needs_r1 && !d->r1) return PCODEC_ERR_BAD_ARG;
   if (epi == PCODEC_EPI_GATE && !d->r2) return PCODEC_ERR_BAD_ARG;
   if ((d->flags & PCODEC_FLAG_PIXEL_SHUFFLE2) && needs_r1) return PCODEC_ERR_UNSUPPORTED;
+  if ((d->flags & PCODEC_FLAG_SUBPIXEL_NCHW) && (needs_r1 || (d->flags & PCODEC_FLAG_PIXEL_SHUFFLE2) || d->out_step != 1))
+    return PCODEC_ERR_UNSUPPORTED;
   return PCODEC_OK;
 }
 
@@ -288,6 +290,7 @@ extern "C" int pcodec_conv_taps(const pcodec_conv_desc *desc, int impl, void *st
     if (!pcodec_conv_taps_tc_supported(desc)) return PCODEC_ERR_UNSUPPORTED;
     return pcodec_conv_taps_tc(desc, stream);
   }
+  if (desc->flags & PCODEC_FLAG_SUBPIXEL_NCHW) return PCODEC_ERR_UNSUPPORTED;  // tcgen05 kernel only
   ConvParams P;
   P.d = *desc;
   P.M = (int64_t)desc->batch * desc->grid_h * desc->grid_w;

@@ -496,7 +496,39 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     for (int j = 0; j < P.n_hi_acc; ++j)
       if (n_steps > j) acc_mask |= 1u << j;
     if (split) acc_mask |= 1u << P.n_hi_acc;
-    if (!shuffle) {
+    if (d.flags & PCODEC_FLAG_SUBPIXEL_NCHW) {
+      // Image layer: conv channel (2*py + px) * C + c  ->  out[n][c][2h + py][2w + px] (NCHW, out_h x out_w = 2 x grid).
+      // A thread owns pixel (h, w); consecutive lanes are consecutive w, so each (c, py) is one 8-byte store per lane
+      // and 256 contiguous bytes per warp.  cout <= 16: a single 16-column chunk, done by warps 0-3.
+      const int Cimg = d.out_pixel_stride;  // image channels (3)
+      if (third == 0) {
+        float acc[16];
+        tmem_ld16(lane_addr, acc);
+        for (int a = 1; a < n_acc; ++a) {
+          if (!((acc_mask >> a) & 1u)) continue;
+          float part[16];
+          tmem_ld16(lane_addr + (uint32_t)(a * bn), part);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += part[j];
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = tc_epilogue(d.epilogue, acc[j] + (d.bias ? __ldg(d.bias + j) : 0.f), 0.f, 0.f, false);
+          const int64_t plane = (int64_t)d.out_h * d.out_w;
+          for (int c = 0; c < Cimg && c < 4; ++c)
+            for (int py = 0; py < 2; ++py) {
+              float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {  // static register indexing
+                if (j == (2 * py) * Cimg + c) v0 = acc[j];
+                if (j == (2 * py + 1) * Cimg + c) v1 = acc[j];
+              }
+              float *dst = d.out + (n * Cimg + c) * plane + (int64_t)(2 * h + py) * d.out_w + 2 * w;
+              *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);
+            }
+        }
+      }
+    } else if (!shuffle) {
       // Coalesced epilogue: a thread owns one tile ROW in tensor memory, but rows are `out_pixel_stride` floats
       // apart in global memory, so a row-per-thread store touches 32 lines per instruction.  Each warp therefore
       // transposes its 32 rows x 16 columns through a private 2 KB shared-memory tile (the pipeline stages are
@@ -792,6 +824,9 @@ bool pcodec_conv_taps_tc_supported(const pcodec_conv_desc *d) {
   const TcWeights *h = static_cast<const TcWeights *>(d->tc_weights);
   if (h->cout != d->cout || h->k_total != d->n_taps * d->cin_total) return false;
   if (d->tc_split != 1 && d->tc_split != 3) return false;
+  if (d->flags & PCODEC_FLAG_SUBPIXEL_NCHW)  // out_pixel_stride = image channels; float2 stores
+    return d->cout == 16 && d->out_pixel_stride >= 1 && d->out_pixel_stride <= 4 && 4 * d->out_pixel_stride <= 16 &&
+           (reinterpret_cast<uintptr_t>(d->out) & 7) == 0 && (d->out_w & 1) == 0;
   // float4 epilogue accesses
   if ((d->out_pixel_stride & 3) || (reinterpret_cast<uintptr_t>(d->out) & 15)) return false;
   if (d->r1 && ((d->r1_pixel_stride & 3) || (reinterpret_cast<uintptr_t>(d->r1) & 15))) return false;

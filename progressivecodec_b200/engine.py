@@ -124,7 +124,8 @@ class Arena:
 class PackedConv:
     """Weights of one tap-GEMM: fp32 [T][Cin][Cout] + bias + tap offsets."""
 
-    __slots__ = ("w", "bias", "taps", "cin", "cout", "in_step", "out_step", "off", "name", "tc", "tc_split")
+    __slots__ = ("w", "bias", "taps", "cin", "cout", "in_step", "out_step", "off", "name", "tc", "tc_split",
+                 "image_channels")
 
     def __init__(self, w: Tensor, bias: Optional[Tensor], taps: Sequence[Tuple[int, int]], in_step=1, out_step=1,
                  off=(0, 0), name=""):
@@ -137,6 +138,7 @@ class PackedConv:
         self.name = name
         self.tc = None       # opaque handle from pcodec_conv_tc_prepare (tcgen05 path)
         self.tc_split = 3
+        self.image_channels = 0  # set by pack_deconv_merged_image
 
     def attach_tc(self, split: int = 3) -> "PackedConv":
         """Build the TF32 hi/lo K-major weights + TMA maps for the tcgen05 kernel (no-op when unsupported,
@@ -210,6 +212,33 @@ def pack_deconv_phases(m: nn.ConvTranspose2d, device, name="", pad_cout_to: int 
             phases.append(PackedConv(torch.stack(mats, 0), b, taps, in_step=1, out_step=2, off=(py, px),
                                      name=f"{name}.phase{py}{px}"))
     return phases
+
+
+def pack_deconv_merged_image(m: nn.ConvTranspose2d, device, name="") -> PackedConv:
+    """Image layer (ConvTranspose2d k5 s2 p2 op1, Cout <= 4) as ONE 9-tap GEMM over the 3x3 input neighbourhood with
+    16 output columns: column (2*py + px) * Cout + c holds sub-pixel phase (py, px) of channel c (zero weights where a
+    phase does not use a tap).  The four phase launches re-read the 192-channel input 25 times for a handful of
+    output channels; merged, it is read 9 times and the result goes straight to the NCHW image."""
+    assert m.kernel_size == (5, 5) and m.stride == (2, 2) and m.padding == (2, 2) and m.output_padding == (1, 1)
+    w = m.weight.detach().to(device=device, dtype=torch.float32)  # [Cin, Cout, 5, 5]
+    cin, cout = w.shape[0], w.shape[1]
+    assert 4 * cout <= 16
+    taps = [(dy, dx) for dy in (1, 0, -1) for dx in (1, 0, -1)]
+    packed = torch.zeros((9, cin, 16), dtype=torch.float32, device=device)
+    bias = torch.zeros(16, dtype=torch.float32, device=device)
+    b = m.bias.detach().to(device=device, dtype=torch.float32) if m.bias is not None else None
+    for py in (0, 1):
+        for px in (0, 1):
+            col = (2 * py + px) * cout
+            if b is not None:
+                bias[col:col + cout] = b
+            for t, (dy, dx) in enumerate(taps):
+                a, bb = 1 - dy, 1 - dx  # input (h + 1 - a, w + 1 - b) <-> kernel tap (py + 2a, px + 2b)
+                if a < (3 if py == 0 else 2) and bb < (3 if px == 0 else 2):
+                    packed[t, :, col:col + cout] = w[:, :, py + 2 * a, px + 2 * bb]
+    pc = PackedConv(packed, bias, taps, in_step=1, out_step=1, name=f"{name}.merged")
+    pc.image_channels = cout
+    return pc
 
 
 def pack_gdn(g, device, name="") -> PackedConv:
@@ -359,6 +388,35 @@ class Engine:
             out = self.act(x.B, 2 * x.H, 2 * x.W, phases[0].cout)
         for ph in phases:
             self.conv(ph, [x], out, epi)
+        return out
+
+    def deconv_image(self, pc: PackedConv, x: Act, epi: int) -> Tensor:
+        """Merged-phase image layer (pack_deconv_merged_image): NHWC activation -> NCHW image [B, C, 2H, 2W]."""
+        Cimg = pc.image_channels
+        out = torch.empty((x.B, Cimg, 2 * x.H, 2 * x.W), dtype=torch.float32, device=self.device)
+        tls = self._state()
+        key = ("img", id(pc), pc.tc, pc.tc_split, x.ptr, x.ps, x.B, x.H, x.W, epi)
+        d = tls.descs.get(key)
+        if d is None:
+            d = L.ConvDesc()
+            d.seg[0].ptr, d.seg[0].channels, d.seg[0].pixel_stride = x.ptr, x.C, x.ps
+            d.n_segments = 1
+            d.batch, d.in_h, d.in_w = x.B, x.H, x.W
+            d.n_taps = len(pc.taps)
+            for t, (dy, dx) in enumerate(pc.taps):
+                d.dy[t], d.dx[t] = dy, dx
+            d.in_step = 1
+            d.weight, d.bias = pc.w.data_ptr(), pc.bias.data_ptr()
+            d.cin_total, d.cout = pc.cin, pc.cout
+            d.grid_h, d.grid_w = x.H, x.W
+            d.out_step, d.out_off_y, d.out_off_x = 1, 0, 0
+            d.out_h, d.out_w = 2 * x.H, 2 * x.W
+            d.out_pixel_stride = Cimg
+            d.epilogue, d.flags = epi, L.FLAG_SUBPIXEL_NCHW
+            d.tc_weights, d.tc_split = pc.tc, pc.tc_split
+            tls.descs[key] = d
+        d.out = out.data_ptr()
+        L.check(self.lib.pcodec_conv_taps(d, self.conv_impl, tls.stream), pc.name)
         return out
 
     def gdn_new(self, pc: PackedConv, x: Act, inverse: bool) -> Act:

@@ -27,8 +27,8 @@ from torch import Tensor
 
 from . import _lib as L
 from . import ans as _ans
-from .engine import (Act, Engine, PackedConv, new_act, pack_conv2d, pack_deconv_phases, pack_first_conv_im2col,
-                     pack_gdn, pack_linear)
+from .engine import (Act, Engine, PackedConv, new_act, pack_conv2d, pack_deconv_merged_image, pack_deconv_phases,
+                     pack_first_conv_im2col, pack_gdn, pack_linear)
 from .entropy_models import EntropyBottleneck, GaussianConditional
 from .layers import (GDN, ChannelMask, Win_noShift_Attention, conv, conv3x3, deconv, subpel_conv3x3)
 
@@ -221,7 +221,8 @@ class ChannelProgresssiveWACNN(nn.Module):
                     "g2": pack_gdn(seq[2], dev, f"{name}.2"), "d3": pack_deconv_phases(seq[3], dev, f"{name}.3"),
                     "g4": pack_gdn(seq[4], dev, f"{name}.4"), "w5": win(seq[5], f"{name}.5"),
                     "d6": pack_deconv_phases(seq[6], dev, f"{name}.6"), "g7": pack_gdn(seq[7], dev, f"{name}.7"),
-                    "d8": pack_deconv_phases(seq[8], dev, f"{name}.8", pad_cout_to=16 if self.tensor_cores else 0)}
+                    "d8": (pack_deconv_merged_image(seq[8], dev, f"{name}.8") if self.tensor_cores
+                           else pack_deconv_phases(seq[8], dev, f"{name}.8"))}
 
         def hyper_s(seq, name):
             return [pack_conv2d(seq[0], dev, f"{name}.0"), pack_conv2d(seq[2][0], dev, f"{name}.2.0"),
@@ -339,8 +340,11 @@ class ChannelProgresssiveWACNN(nn.Module):
             h = self._win(E, pk["w5"], h)
             h = E.deconv_new(pk["d6"], h)
             h = E.gdn_new(pk["g7"], h, True)
-            h = E.deconv_new(pk["d8"], h, L.EPI_CLAMP01 if clamp else L.EPI_LINEAR)
-            return E.to_nchw(h.slice(0, 3))  # the image layer may be zero-padded to 16 channels for the TC kernel
+            epi = L.EPI_CLAMP01 if clamp else L.EPI_LINEAR
+            if isinstance(pk["d8"], PackedConv):  # merged sub-pixel phases, written straight to the NCHW image
+                return E.deconv_image(pk["d8"], h, epi)
+            h = E.deconv_new(pk["d8"], h, epi)
+            return E.to_nchw(h)
 
     def _h_a(self, P, y: Act) -> Act:
         E = P["eng"]

@@ -280,3 +280,22 @@ def test_tc_conv_is_batch_invariant_and_deterministic():
     assert torch.equal(full, _nchw(E.conv_new(pc, [_nhwc(x)])))
     for b in (0, 3, 4):
         assert torch.equal(_nchw(E.conv_new(pc, [_nhwc(x[b:b + 1])]))[0], full[b])
+
+
+@pytest.mark.parametrize("hw,batch", [((32, 48), 2), ((7, 9), 3), ((64, 96), 1)])
+def test_tc_merged_image_layer(hw, batch):
+    """deconv(N, 3) of g_s as ONE 9-tap GEMM (4 sub-pixel phases in 12 of 16 columns) written straight to NCHW."""
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import pack_deconv_merged_image
+
+    E = _engine()
+    torch.manual_seed(hw[0])
+    m = nn.ConvTranspose2d(192, 3, 5, 2, 2, 1)
+    x = torch.randn(batch, 192, *hw)
+    ref = m(x).detach()
+    pc = pack_deconv_merged_image(m, E.device, "img").attach_tc(3)
+    assert pc.tc is not None
+    got = E.deconv_image(pc, _nhwc(x), L.EPI_LINEAR)
+    assert got.shape == ref.shape
+    _close(got.cpu(), ref)
+    _close(E.deconv_image(pc, _nhwc(x), L.EPI_CLAMP01).cpu(), ref.clamp(0, 1))
