@@ -77,6 +77,30 @@ int pcodec_rans_decode_batch(const uint8_t *in_bytes, const int64_t *in_offsets,
                              const int32_t *indexes, const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes,
                              const int32_t *offsets, int n_tables, int32_t *out_symbols, void *stream);
 
+/* Variable-length streams ("segments") for the truncatable progressive container (the reference has
+ * no container format — its compress() returns python lists, CHProg_cnn.py:847).  Stream s codes the elements
+ * [seg_start[s], seg_start[s] + seg_count[s]) of the flat symbols / indexes arrays with the same arithmetic as
+ * pcodec_rans_encode_batch (each segment is a stand-alone reference-decodable rANS stream). */
+int pcodec_rans_encode_segments(const int32_t *symbols, const int32_t *indexes, const int64_t *seg_start,
+                                const int32_t *seg_count, int n_streams, const int32_t *cdfs, int cdf_stride,
+                                const int32_t *cdf_sizes, const int32_t *offsets, int n_tables, uint32_t *scratch,
+                                int64_t scratch_words, int32_t *n_words, uint8_t *out_bytes, int64_t out_cap,
+                                int64_t *out_offsets, int32_t *status, void *stream);
+int pcodec_rans_decode_segments(const uint8_t *in_bytes, const int64_t *starts, const int64_t *ends, int n_streams,
+                                const int64_t *seg_start, const int32_t *seg_count, const int32_t *indexes,
+                                const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
+                                int n_tables, int32_t *out_symbols, void *stream);
+
+/* Progressive-layer partition of one 32-channel slice (replaces nothing in the reference: it turns the nested
+ * variance-aware masks of masking.py:205-223 into an embedded layer order).  thresholds: float [n_levels][batch] in
+ * non-increasing order per image (NaN = "everything", i.e. pr >= 10).  layer(e) = #{k : sigma_e < thr_k}.
+ *   scatter == 0: in_a / in_b (NCHW-order planes int32 [batch][channels*hw], either may be NULL) are stably
+ *                 partitioned by layer into out_a / out_b; counts int32 [batch][16] receives the layer sizes.
+ *   scatter != 0: in_a holds layer-major compacted values; out_a[e] = value if layer(e) < avail[b] else 0. */
+int pcodec_layer_partition(const float *sigma, int sigma_ps, int batch, int64_t hw, int channels, const float *thresholds,
+                           int n_levels, const int32_t *in_a, const int32_t *in_b, int32_t *out_a, int32_t *out_b,
+                           int32_t *counts, const int32_t *avail, int scatter, void *stream);
+
 /* Same decoder for streams that are NOT consecutive in in_bytes: stream s occupies bytes [starts[s], ends[s]).  Lets
  * one launch decode several slices of a sub-batch (e.g. base slices 5..9, whose parameters do not depend on each
  * other, CHProg_cnn.py:878) out of a slice-major stream container. */

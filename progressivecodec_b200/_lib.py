@@ -61,6 +61,9 @@ PROTOTYPES = {
     "pcodec_rans_encode_batch": (_i, [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _i, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "pcodec_rans_decode_batch": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "pcodec_rans_decode_ranges": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "pcodec_rans_encode_segments": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "pcodec_rans_decode_segments": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "pcodec_layer_partition": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pcodec_selftest_rans_core_encode": (_i64, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _i64]),
     "pcodec_quantile_threshold": (_i, [_vp, _i, _i64, _i, _i, _f, _vp, _vp, _vp]),
     "pcodec_slice_quantize": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp, _vp, _i, _f,

@@ -105,6 +105,52 @@ def decode_ranges(data: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor, 
     return out
 
 
+def encode_segments(symbols: torch.Tensor, indexes: torch.Tensor, seg_start: torch.Tensor, seg_count: torch.Tensor,
+                    tables: CdfTables, max_count: int, words_per_symbol: float = 0.5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Variable-length streams: stream s codes elements [seg_start[s], seg_start[s]+seg_count[s]) of the flat int32
+    CUDA arrays.  seg_start int64 / seg_count int32 CUDA tensors [S].  Returns (bytes, int64 CPU offsets [S+1])."""
+    assert symbols.is_cuda and indexes.is_cuda and seg_start.is_cuda and seg_count.is_cuda
+    assert seg_start.dtype == torch.int64 and seg_count.dtype == torch.int32
+    symbols, indexes = symbols.contiguous(), indexes.contiguous()
+    S = seg_start.numel()
+    dev = symbols.device
+    lib = L.lib()
+    while True:
+        cap_words = int(max_count * words_per_symbol) + 16
+        scratch = torch.empty((S, cap_words), dtype=torch.int32, device=dev)
+        n_words = torch.empty((S,), dtype=torch.int32, device=dev)
+        out_cap = S * cap_words * 4
+        out = torch.empty((out_cap,), dtype=torch.uint8, device=dev)
+        meta = torch.empty((S + 2,), dtype=torch.int64, device=dev)
+        status = meta[S + 1:].view(torch.int32)
+        L.check(lib.pcodec_rans_encode_segments(symbols.data_ptr(), indexes.data_ptr(), seg_start.data_ptr(),
+                                                seg_count.data_ptr(), S, tables.cdfs.data_ptr(), tables.cdfs.shape[1],
+                                                tables.sizes.data_ptr(), tables.offsets.data_ptr(), tables.cdfs.shape[0],
+                                                scratch.data_ptr(), cap_words, n_words.data_ptr(), out.data_ptr(), out_cap,
+                                                meta.data_ptr(), status.data_ptr(), _stream()), "rans_encode_segments")
+        host = meta.cpu()
+        if int(host[S + 1:].view(torch.int32)[0]) == L.ERR_OVERFLOW:
+            if words_per_symbol >= 6.0:
+                raise L.PcodecError("rans_encode_segments: stream exceeds 6 words/symbol")
+            words_per_symbol = min(6.0, words_per_symbol * 4)
+            continue
+        offsets = host[: S + 1]
+        return out[: int(offsets[S])], offsets
+
+
+def decode_segments(data: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor, seg_start: torch.Tensor,
+                    seg_count: torch.Tensor, indexes: torch.Tensor, out: torch.Tensor, tables: CdfTables) -> torch.Tensor:
+    """Inverse of encode_segments: stream s (bytes [starts[s], ends[s]) of `data`) fills out[seg_start[s] : +count]."""
+    assert data.is_cuda and indexes.is_cuda and out.is_cuda and out.dtype == torch.int32 and indexes.dtype == torch.int32
+    S = seg_start.numel()
+    L.check(L.lib().pcodec_rans_decode_segments(data.data_ptr(), starts.data_ptr(), ends.data_ptr(), S,
+                                                seg_start.data_ptr(), seg_count.data_ptr(), indexes.data_ptr(),
+                                                tables.cdfs.data_ptr(), tables.cdfs.shape[1], tables.sizes.data_ptr(),
+                                                tables.offsets.data_ptr(), tables.cdfs.shape[0], out.data_ptr(), _stream()),
+            "rans_decode_segments")
+    return out
+
+
 def pack_streams(strings: Sequence[bytes], device) -> Tuple[torch.Tensor, torch.Tensor]:
     """Host byte strings -> (uint8 CUDA blob with 8 bytes of zero slack, int64 CPU offsets)."""
     lens = [len(s) for s in strings]

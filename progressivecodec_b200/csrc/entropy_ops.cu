@@ -385,6 +385,86 @@ inline dim3 tile_grid(int64_t hw, int channels, int batch) {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// Progressive-layer partition (truncatable container)
+// ------------------------------------------------------------------------------------------------
+// The variance-aware masks of increasing quality levels are nested (thr_0 >= thr_1 >= ...), so every latent element
+// of a progressive slice ENTERS at exactly one level: layer(e) = #{k : sigma_e < thr_k}.  One CTA per image stably
+// partitions the slice's elements (in the coder's NCHW order) by layer:
+//   gather : raster planes (symbols, indexes) -> layer-major compacted arrays + per-layer counts
+//   scatter: decoded compacted symbols of the first `avail` layers -> raster plane (zeros elsewhere)
+// Both directions compute (layer, rank) identically, so the decoder recovers the encoder's order from sigma alone.
+constexpr int kMaxLayers = 15;  // + 1 bucket for "never enters"
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(1024)
+layer_partition_kernel(const float *__restrict__ sigma, int sigma_ps, int64_t hw, int channels,
+                       const float *__restrict__ thr /* [n_levels][batch] */, int n_levels, int batch,
+                       const int32_t *__restrict__ in_a, const int32_t *__restrict__ in_b,
+                       int32_t *__restrict__ out_a, int32_t *__restrict__ out_b, int32_t *__restrict__ counts,
+                       const int32_t *__restrict__ avail) {
+  __shared__ int s_hist[kMaxLayers + 1];
+  __shared__ int s_base[kMaxLayers + 1];
+  __shared__ int s_warp[32][kMaxLayers + 1];
+  __shared__ float s_thr[kMaxLayers];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = hw * channels;
+  const float *sg = sigma + (int64_t)b * hw * sigma_ps;
+  if (tid <= kMaxLayers) s_hist[tid] = 0;
+  if (tid < n_levels) s_thr[tid] = thr[(int64_t)tid * batch + b];
+  __syncthreads();
+  auto layer_of = [&](int64_t e) {  // element e = (channel c, pixel p) of the NCHW plane
+    const int64_t c = e / hw, p = e - c * hw;
+    const float v = sg[p * sigma_ps + c];
+    int k = 0;
+    for (int l = 0; l < n_levels; ++l) k += (v < s_thr[l]) ? 1 : 0;  // NaN thresholds (pr >= 10: "ones") never exclude
+    return k;
+  };
+  // pass 1: histogram
+  for (int64_t e = tid; e < n; e += blockDim.x) atomicAdd(&s_hist[layer_of(e)], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k <= n_levels; ++k) { s_base[k] = run; run += s_hist[k]; }
+  }
+  __syncthreads();
+  if (!SCATTER && counts && tid <= n_levels) counts[(int64_t)b * (kMaxLayers + 1) + tid] = s_hist[tid];
+  const int n_avail = SCATTER ? avail[b] : 0;
+  const int64_t row = (int64_t)b * n;
+  // pass 2: chunks of 1024 consecutive elements; rank inside the chunk by per-layer ballots
+  for (int64_t e0 = 0; e0 < n; e0 += blockDim.x) {
+    const int64_t e = e0 + tid;
+    const bool ok = e < n;
+    const int k = ok ? layer_of(e) : -1;
+    int my_rank = 0;
+    for (int l = 0; l <= n_levels; ++l) {
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, k == l);
+      if (k == l) my_rank = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) s_warp[warp][l] = __popc(m);
+    }
+    __syncthreads();
+    if (ok) {
+      int before = 0;
+      for (int w = 0; w < warp; ++w) before += s_warp[w][k];
+      const int64_t pos = row + s_base[k] + before + my_rank;
+      if (!SCATTER) {
+        if (in_a) out_a[pos] = in_a[row + e];
+        if (in_b) out_b[pos] = in_b[row + e];
+      } else {
+        out_a[row + e] = k < n_avail ? in_a[pos] : 0;
+      }
+    }
+    __syncthreads();
+    if (tid <= n_levels) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += s_warp[w][tid];
+      s_base[tid] += tot;
+    }
+    __syncthreads();
+  }
+}
+
 extern "C" int pcodec_quantile_threshold(const float *scale, int batch, int64_t hw, int channels, int pixel_stride,
                                          float q, float *thr, uint32_t *workspace, void *stream) {
   (void)workspace;
@@ -470,5 +550,25 @@ extern "C" int pcodec_nhwc_to_nchw(const float *src, int src_ps, float *dst, int
   if (!src || !dst || batch <= 0 || hw <= 0 || channels <= 0) return PCODEC_ERR_BAD_ARG;
   nhwc_to_nchw_kernel<<<tile_grid(hw, channels, batch), dim3(32, 8), 0, as_stream(stream)>>>(src, src_ps, dst,
                                                                                              channels, hw);
+  PCODEC_RETURN_LAUNCH();
+}
+
+extern "C" int pcodec_layer_partition(const float *sigma, int sigma_ps, int batch, int64_t hw, int channels,
+                                      const float *thresholds, int n_levels, const int32_t *in_a, const int32_t *in_b,
+                                      int32_t *out_a, int32_t *out_b, int32_t *counts, const int32_t *avail,
+                                      int scatter, void *stream) {
+  if (!sigma || !thresholds || batch <= 0 || hw <= 0 || channels <= 0 || n_levels < 1 || n_levels > kMaxLayers)
+    return PCODEC_ERR_BAD_ARG;
+  if (scatter) {
+    if (!in_a || !out_a || !avail) return PCODEC_ERR_BAD_ARG;
+    layer_partition_kernel<true><<<batch, 1024, 0, as_stream(stream)>>>(sigma, sigma_ps, hw, channels, thresholds,
+                                                                          n_levels, batch, in_a, nullptr, out_a, nullptr,
+                                                                          nullptr, avail);
+  } else {
+    if ((in_a && !out_a) || (in_b && !out_b) || !counts) return PCODEC_ERR_BAD_ARG;
+    layer_partition_kernel<false><<<batch, 1024, 0, as_stream(stream)>>>(sigma, sigma_ps, hw, channels, thresholds,
+                                                                           n_levels, batch, in_a, in_b, out_a, out_b,
+                                                                           counts, nullptr);
+  }
   PCODEC_RETURN_LAUNCH();
 }

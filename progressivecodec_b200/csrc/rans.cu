@@ -37,12 +37,16 @@ rans_encode_kernel(const int32_t *__restrict__ symbols, const int32_t *__restric
                    int64_t n, const int32_t *__restrict__ cdfs, int cdf_stride,
                    const int32_t *__restrict__ cdf_sizes, const int32_t *__restrict__ offsets,
                    uint32_t *__restrict__ scratch, int64_t scratch_words, int32_t *__restrict__ n_words_out,
-                   int32_t *__restrict__ status) {
+                   int32_t *__restrict__ status, const int64_t *__restrict__ seg_start,
+                   const int32_t *__restrict__ seg_count) {
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (s >= n_streams) return;
-  const int32_t *sym = symbols + (int64_t)s * n;
-  const int32_t *idx = indexes + (int64_t)s * n;
+  // segment mode: stream s = elements [seg_start[s], seg_start[s] + seg_count[s]) of the flat symbol / index arrays
+  const int64_t first = seg_start ? seg_start[s] : (int64_t)s * n;
+  if (seg_count) n = seg_count[s];
+  const int32_t *sym = symbols + first;
+  const int32_t *idx = indexes + first;
   uint32_t *out = scratch + (int64_t)s * scratch_words;
   int64_t wpos = scratch_words;  // next free slot is wpos-1 (stream grows downwards)
   bool overflow = false;
@@ -238,14 +242,18 @@ rans_decode_kernel(const uint8_t *__restrict__ in_bytes, const int64_t *__restri
                    const int64_t *__restrict__ in_ends, int n_streams,
                    int64_t n, const int32_t *__restrict__ indexes, const int32_t *__restrict__ cdfs, int cdf_stride,
                    const int32_t *__restrict__ cdf_sizes, const int32_t *__restrict__ offsets,
-                   int32_t *__restrict__ out_symbols) {
+                   int32_t *__restrict__ out_symbols, const int64_t *__restrict__ seg_start,
+                   const int32_t *__restrict__ seg_count) {
   __shared__ DecChunk buf[2];
   __shared__ int32_t s_val[64];  // [0,32): decoded slot per symbol of the chunk; [32,64): dummy slots
   const int lane = threadIdx.x & 31;
   const int role = threadIdx.x >> 5;  // 0,1 = producers (symbols 0-15 / 16-31 of a chunk), 2 = walker
   const int s = blockIdx.x;
-  const int32_t *idx = indexes + (int64_t)s * n;
-  int32_t *out = out_symbols + (int64_t)s * n;
+  const int64_t first = seg_start ? seg_start[s] : (int64_t)s * n;
+  if (seg_count) n = seg_count[s];
+  if (n <= 0) return;  // empty segment (uniform for the CTA)
+  const int32_t *idx = indexes + first;
+  int32_t *out = out_symbols + first;
   const int64_t n_chunks = (n + 31) / 32;
 
   WordReader rd;
@@ -393,7 +401,7 @@ extern "C" int pcodec_rans_encode_batch(const int32_t *symbols, const int32_t *i
   const int blocks = (n_streams + kWarpsPerBlock - 1) / kWarpsPerBlock;
   rans_encode_kernel<<<blocks, 32 * kWarpsPerBlock, 0, st>>>(symbols, indexes, n_streams, n_per_stream, cdfs,
                                                               cdf_stride, cdf_sizes, offsets, scratch, scratch_words,
-                                                              n_words, status);
+                                                              n_words, status, nullptr, nullptr);
   PCODEC_COUNT_LAUNCH();
   rans_offsets_kernel<<<1, 1024, 0, st>>>(n_words, n_streams, out_offsets, out_cap, status);
   PCODEC_COUNT_LAUNCH();
@@ -414,7 +422,7 @@ extern "C" int pcodec_rans_decode_batch(const uint8_t *in_bytes, const int64_t *
   if (!indexes || !out_symbols) return PCODEC_ERR_BAD_ARG;
   rans_decode_kernel<<<n_streams, kDecThreads, 0, as_stream(stream)>>>(
       in_bytes, in_offsets, in_offsets + 1, n_streams, n_per_stream, indexes, cdfs, cdf_stride, cdf_sizes, offsets,
-      out_symbols);
+      out_symbols, nullptr, nullptr);
   PCODEC_RETURN_LAUNCH();
 }
 
@@ -427,7 +435,61 @@ extern "C" int pcodec_rans_decode_ranges(const uint8_t *in_bytes, const int64_t 
   if (n_per_stream == 0) return PCODEC_OK;
   if (!indexes || !out_symbols) return PCODEC_ERR_BAD_ARG;
   rans_decode_kernel<<<n_streams, kDecThreads, 0, as_stream(stream)>>>(
-      in_bytes, starts, ends, n_streams, n_per_stream, indexes, cdfs, cdf_stride, cdf_sizes, offsets, out_symbols);
+      in_bytes, starts, ends, n_streams, n_per_stream, indexes, cdfs, cdf_stride, cdf_sizes, offsets, out_symbols,
+      nullptr, nullptr);
+  PCODEC_RETURN_LAUNCH();
+}
+
+// Variable-length streams ("segments") of flat symbol / index arrays: the progressive container codes, per (layer,
+// slice, image), only the latent elements that ENTER at that layer.
+extern "C" int pcodec_rans_encode_segments(const int32_t *symbols, const int32_t *indexes, const int64_t *seg_start,
+                                           const int32_t *seg_count, int n_streams, const int32_t *cdfs, int cdf_stride,
+                                           const int32_t *cdf_sizes, const int32_t *offsets, int n_tables,
+                                           uint32_t *scratch, int64_t scratch_words, int32_t *n_words,
+                                           uint8_t *out_bytes, int64_t out_cap, int64_t *out_offsets, int32_t *status,
+                                           void *stream) {
+  (void)n_tables;
+  if (n_streams <= 0 || scratch_words < 2 || !scratch || !n_words || !out_bytes || !out_offsets || !status || !symbols ||
+      !indexes || !seg_start || !seg_count)
+    return PCODEC_ERR_BAD_ARG;
+  cudaStream_t st = as_stream(stream);
+  {
+    static std::atomic<uint64_t> built_mask{0};
+    int dev = 0;
+    PCODEC_CHECK_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(built_mask.load() & bit)) {
+      rans_build_rcp_kernel<<<256, 256, 0, st>>>();
+      PCODEC_COUNT_LAUNCH();
+      PCODEC_CHECK_CUDA(cudaStreamSynchronize(st));
+      built_mask.fetch_or(bit);
+    }
+  }
+  PCODEC_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  rans_encode_kernel<<<n_streams, 32 * kWarpsPerBlock, 0, st>>>(symbols, indexes, n_streams, 0, cdfs, cdf_stride,
+                                                                 cdf_sizes, offsets, scratch, scratch_words, n_words,
+                                                                 status, seg_start, seg_count);
+  PCODEC_COUNT_LAUNCH();
+  rans_offsets_kernel<<<1, 1024, 0, st>>>(n_words, n_streams, out_offsets, out_cap, status);
+  PCODEC_COUNT_LAUNCH();
+  rans_compact_kernel<<<dim3(n_streams, 4), 256, 0, st>>>(scratch, scratch_words, n_words, out_offsets, n_streams,
+                                                          out_bytes, out_cap);
+  PCODEC_COUNT_LAUNCH();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PCODEC_OK : -(int)e;
+}
+
+extern "C" int pcodec_rans_decode_segments(const uint8_t *in_bytes, const int64_t *starts, const int64_t *ends,
+                                           int n_streams, const int64_t *seg_start, const int32_t *seg_count,
+                                           const int32_t *indexes, const int32_t *cdfs, int cdf_stride,
+                                           const int32_t *cdf_sizes, const int32_t *offsets, int n_tables,
+                                           int32_t *out_symbols, void *stream) {
+  (void)n_tables;
+  if (n_streams <= 0 || !in_bytes || !starts || !ends || !seg_start || !seg_count || !indexes || !out_symbols)
+    return PCODEC_ERR_BAD_ARG;
+  rans_decode_kernel<<<n_streams, kDecThreads, 0, as_stream(stream)>>>(
+      in_bytes, starts, ends, n_streams, 0, indexes, cdfs, cdf_stride, cdf_sizes, offsets, out_symbols, seg_start,
+      seg_count);
   PCODEC_RETURN_LAUNCH();
 }
 

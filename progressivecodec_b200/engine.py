@@ -475,6 +475,18 @@ class Engine:
                                                table.data_ptr(), table.numel(), bound, p(symbols), p(indexes),
                                                p(mask_out), p(lik), ap(y_hat), aps(y_hat), self.stream()), "slice_quantize")
 
+    def layer_partition(self, scale: Act, thresholds: Tensor, in_a: Optional[Tensor], in_b: Optional[Tensor],
+                        out_a: Optional[Tensor], out_b: Optional[Tensor], counts: Optional[Tensor],
+                        avail: Optional[Tensor] = None) -> None:
+        """Stable partition of a slice's NCHW-order planes by progressive layer (gather), or its inverse (scatter,
+        when `avail` is given).  thresholds: float32 [n_levels, B]; counts: int32 [B, 16]."""
+        p = lambda t: t.data_ptr() if t is not None else None
+        assert thresholds.dtype == torch.float32 and thresholds.is_contiguous() and thresholds.shape[1] == scale.B
+        L.check(self.lib.pcodec_layer_partition(scale.ptr, scale.ps, scale.B, scale.H * scale.W, scale.C,
+                                                thresholds.data_ptr(), thresholds.shape[0], p(in_a), p(in_b), p(out_a),
+                                                p(out_b), p(counts), p(avail), 1 if avail is not None else 0,
+                                                self.stream()), "layer_partition")
+
     def slice_dequantize(self, symbols: Tensor, mu: Act, y_hat: Act) -> None:
         L.check(self.lib.pcodec_slice_dequantize(symbols.data_ptr(), mu.ptr, mu.ps, mu.B, mu.H * mu.W, mu.C, y_hat.ptr,
                                                  y_hat.ps, self.stream()), "slice_dequantize")

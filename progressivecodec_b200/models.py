@@ -400,8 +400,10 @@ class ChannelProgresssiveWACNN(nn.Module):
         more than 4 segments remain (only the `all_scalable` + forward_single_quality bookkeeping quirk)."""
         out: List[Act] = []
         for a in acts:
-            if out and out[-1].t is a.t and out[-1].c0 + out[-1].C == a.c0:
-                out[-1] = Act(a.t, out[-1].c0, out[-1].C + a.C)
+            p = out[-1] if out else None
+            if (p is not None and p.base == a.base and p.ps == a.ps and (p.B, p.H, p.W) == (a.B, a.H, a.W)
+                    and p.c0 + p.C == a.c0):
+                out[-1] = p.slice(0, p.C + a.C)  # same buffer, adjacent channel window
             else:
                 out.append(a)
         if len(out) > L.MAX_SEGMENTS:
@@ -458,7 +460,7 @@ class ChannelProgresssiveWACNN(nn.Module):
         return y_hat_base
 
     def _prog_slices(self, P, lm: Act, ls: Act, y_hat_base: Act, quality, mask_pol, code, mode: str,
-                     state: Optional[dict] = None, residual_before_lrp: bool = False):
+                     state: Optional[dict] = None, residual_before_lrp: bool = False, deferred: Optional[list] = None):
         """Progressive loop (CHProg_cnn.py:576-642 / 775-845 / 921-983 / 1091-1166).
         `code(i, mu, scale, mask_mode, thr, y_pre)`; `mode` in {"forward","fsq","codec"} selects the
         mu_total / std_total bookkeeping of that entry point (only observable with all_scalable)."""
@@ -518,10 +520,19 @@ class ChannelProgresssiveWACNN(nn.Module):
                 y_pre = Act((y_pre.dense() + base_i.dense()).contiguous())
                 self._stack(E, P["lrp_transforms_prog"][i], self._merge_segments(E, mean_sup + [y_pre]), out_i,
                             L.EPI_LRP, r1=y_pre)
+            elif deferred is not None:
+                # all_scalable: nothing below depends on this slice's symbols, so the caller may entropy-decode every
+                # slice in one launch and run the LRP stacks afterwards (progressive container, container.py)
+                deferred.append((i, mean_sup + [y_pre], out_i, y_pre, base_i))
             else:
                 self._stack(E, P["lrp_transforms_prog"][i], self._merge_segments(E, mean_sup + [y_pre]), out_i,
                             L.EPI_LRP, r1=y_pre, r2=base_i)
         return y_hat_q
+
+    def _run_deferred_lrp(self, P, deferred: list) -> None:
+        E = P["eng"]
+        for i, segs, out_i, y_pre, base_i in deferred:  # segments are merged NOW: a materialised concat must see y_pre filled
+            self._stack(E, P["lrp_transforms_prog"][i], self._merge_segments(E, segs), out_i, L.EPI_LRP, r1=y_pre, r2=base_i)
 
     # ------------------------------------------------------------------------------------------------------
     # public API
@@ -762,9 +773,9 @@ class ChannelProgresssiveWACNN(nn.Module):
             outs[g].record_stream(cur)
         return {"x_hat": torch.cat(outs, 0)}
 
-    def _decompress_group(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, quality, mask_pol,
-                          slot: int = 0):
-        """Decode images [lo, hi) of a batch whose streams are laid out slice-major: stream (s, b) = s*B_total + b."""
+    def _decode_base(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, enhanced: bool, slot: int):
+        """z + the 10 base slices of images [lo, hi) of a batch whose streams are laid out slice-major
+        (stream (s, b) = s*B_total + b).  Returns (lm, ls, y_hat_base, decode_slice)."""
         E: Engine = P["eng"]
         dev = E.device
         E.begin(slot)
@@ -775,7 +786,7 @@ class ChannelProgresssiveWACNN(nn.Module):
         z_sym = _ans.decode_batch(z_data, z_off_dev[lo:hi + 1], z_idx, P["eb_tables"])
         z_hat = E.act(B, hz, wz, Cz)
         E.bottleneck_dequantize(z_sym, P["medians"], z_hat)
-        lm, ls = self._latents(P, z_hat, enhanced=not (quality == 0))
+        lm, ls = self._latents(P, z_hat, enhanced=enhanced)
         h, w = 4 * hz, 4 * wz
         n = 32 * h * w
         table, bound = P["scale_table"], P["scale_bound"]
@@ -802,6 +813,13 @@ class ChannelProgresssiveWACNN(nn.Module):
         y_hat_base = self._base_slices(
             P, lm, ls, lambda i, mu, scale, y_pre: decode_slice(i, scale, L.MASK_ONES, None, mu, y_pre),
             code_many=decode_many if self.batch_independent_slices else None)
+        return lm, ls, y_hat_base, decode_slice
+
+    def _decompress_group(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, quality, mask_pol,
+                          slot: int = 0):
+        """Decode images [lo, hi) of a batch whose streams are laid out slice-major: stream (s, b) = s*B_total + b."""
+        lm, ls, y_hat_base, decode_slice = self._decode_base(P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi,
+                                                             shape, enhanced=not (quality == 0), slot=slot)
         if quality == 0:
             return self._g_s(P, y_hat_base, 0, clamp=True)
         y_hat_q = self._prog_slices(

@@ -121,3 +121,36 @@ def test_synthetic_weights_are_name_keyed_and_deterministic():
     assert len(shared) > 500
     for k in shared:
         assert torch.equal(sa[k], sb[k]), k
+
+
+def test_container_header_round_trip_and_prefix_logic():
+    """Progressive container header (container.py): pack/parse, prefix offsets, complete-layer detection."""
+    from progressivecodec_b200 import PcodecError
+    from progressivecodec_b200.container import Header, truncate
+
+    levels = [0.05, 1.0, 10.0]
+    hdr = Header(levels, 512, 768, 8, 12, 10, 10, 111, [10 + i for i in range(10)],
+                 [[4 * (k + 1) if i % 2 == 0 else 0 for i in range(10)] for k in range(3)])
+    raw = hdr.pack()
+    assert len(raw) == hdr.size
+    payload_len = hdr.prefix_end(3) - hdr.size
+    blob = raw + bytes(range(256)) * (payload_len // 256 + 1)
+    blob = blob[:hdr.prefix_end(3)]
+    h2 = Header.parse(blob)
+    assert (h2.H, h2.W, h2.zh, h2.zw, h2.n_base, h2.n_prog, h2.z_len) == (512, 768, 8, 12, 10, 10, 111)
+    assert h2.base_len == hdr.base_len and h2.layer_len == hdr.layer_len
+    assert [round(v, 4) for v in h2.levels] == levels
+    ends = [h2.prefix_end(k) for k in range(4)]
+    assert ends == sorted(ends) and ends[3] == len(blob)
+    for k in range(4):
+        assert h2.layers_in(ends[k]) == k
+        assert len(truncate(blob, k)) == ends[k]
+        if k < 3:
+            assert h2.layers_in(ends[k + 1] - 1) == k  # an incomplete layer does not count
+    assert h2.layers_in(ends[0] - 1) == -1
+    import pytest
+
+    with pytest.raises(PcodecError):
+        Header.parse(b"nope" + blob[4:])
+    with pytest.raises(PcodecError):
+        Header.parse(blob[:30])

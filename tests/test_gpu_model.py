@@ -177,3 +177,35 @@ def test_error_behaviour_matches_reference():
     net2, _ = build_pair("authors", "cuda")
     with pytest.raises(NotImplementedError):
         net2.compress(torch.rand(1, 3, 64, 64, device="cuda"), quality=1, mask_pol="no-such-policy")
+
+
+def test_config3_batched_forward_training_crops():
+    """BASELINE config 3: batched forward() on the 16x3x256x256 training-crop shape with variance-aware masking at
+    every quality level.  (a) four levels against the CPU oracle at the full batch: per-level PSNR within 0.02 dB,
+    bpp (from likelihoods) within 0.5 %; (b) the full 13-level list: shapes, rate non-decreasing with quality, and every
+    level's reconstruction equal to forward_single_quality at that level (the reference's own self-consistency)."""
+    net, orc = build_pair("authors", "cuda")
+    x = synthetic_image((16, 3, 256, 256), seed=11)
+    npx = x.shape[0] * x.shape[2] * x.shape[3]
+    pol = "point-based-std"
+    ql = [0, 0.5, 2, 10]
+    o = net.forward(x.cuda(), quality=ql, mask_pol=pol, training=False)
+    r = orc.forward(x, quality=ql, mask_pol=pol)
+    assert o["x_hat"].shape == r["x_hat"].shape == (len(ql), 16, 3, 256, 256)
+    for l in range(len(ql)):
+        a, b = psnr(o["x_hat"][l].cpu().clamp(0, 1), x), psnr(r["x_hat"][l].clamp(0, 1), x)
+        assert abs(a - b) <= 0.02, (ql[l], a, b)
+    for k in ("y", "y_prog", "z"):
+        assert o["likelihoods"][k].shape == r["likelihoods"][k].shape
+        b1 = bpp_from_likelihoods([o["likelihoods"][k].cpu()], npx)
+        b2 = bpp_from_likelihoods([r["likelihoods"][k]], npx)
+        assert abs(b1 - b2) <= 0.005 * b2 + 1e-4, (k, b1, b2)
+    full = list(QUALITIES)
+    o13 = net.forward(x.cuda(), quality=full, mask_pol=pol, training=False)
+    assert o13["x_hat"].shape == (len(full), 16, 3, 256, 256)
+    assert o13["likelihoods"]["y_prog"].shape[0] == len(full) - 1
+    rates = [float(-torch.log2(o13["likelihoods"]["y_prog"][l]).sum()) for l in range(len(full) - 1)]
+    assert all(rates[i + 1] >= rates[i] - 1e-3 * abs(rates[i]) for i in range(len(rates) - 1)), rates
+    for l in (0, 5, len(full) - 1):
+        fsq = net.forward_single_quality(x.cuda(), full[l], mask_pol=pol, training=False)["x_hat"]
+        assert torch.allclose(o13["x_hat"][l].clamp(0, 1), fsq, atol=1e-6), full[l]
