@@ -229,14 +229,33 @@ __device__ __forceinline__ float tc_epilogue(int epi, float acc, float r1, float
   }
 }
 
-// four channels at once, ONE switch: keeps a single copy of every transcendental in the kernel image (the code is
-// fetched cold by every CTA; 16 inlined copies of the scalar switch made the kernel 160 KB of SASS)
+// Four channels at once behind ONE switch: keeps a single copy of every transcendental in the kernel image (the code is
+// fetched cold by every CTA; 16 inlined copies of the scalar switch made the kernel 160 KB of SASS) and lets the four
+// independent chains of a case interleave (the epilogue warps are latency bound, not throughput bound).
 __device__ __noinline__ float4 tc_epilogue4(int epi, float4 v, float4 r1, float4 r2, bool has_r2) {
+#define PC_EACH(expr)                                                                  \
+  do {                                                                                 \
+    { const float a = v.x, p = r1.x, q = r2.x; (void)p; (void)q; o.x = (expr); }        \
+    { const float a = v.y, p = r1.y, q = r2.y; (void)p; (void)q; o.y = (expr); }        \
+    { const float a = v.z, p = r1.z, q = r2.z; (void)p; (void)q; o.z = (expr); }        \
+    { const float a = v.w, p = r1.w, q = r2.w; (void)p; (void)q; o.w = (expr); }        \
+  } while (0)
   float4 o;
-  o.x = tc_epilogue(epi, v.x, r1.x, r2.x, has_r2);
-  o.y = tc_epilogue(epi, v.y, r1.y, r2.y, has_r2);
-  o.z = tc_epilogue(epi, v.z, r1.z, r2.z, has_r2);
-  o.w = tc_epilogue(epi, v.w, r1.w, r2.w, has_r2);
+  switch (epi) {
+    case PCODEC_EPI_GELU: PC_EACH(gelu_erf(a)); break;
+    case PCODEC_EPI_ADD: PC_EACH(a + p); break;
+    case PCODEC_EPI_ADD_GELU: PC_EACH(gelu_erf(a + p)); break;
+    case PCODEC_EPI_GATE: PC_EACH(q * sigmoid_f(a) + p); break;
+    case PCODEC_EPI_GDN: PC_EACH(p * rsqrtf(a)); break;
+    case PCODEC_EPI_IGDN: PC_EACH(p * sqrtf(a)); break;
+    case PCODEC_EPI_LRP:
+      if (has_r2) PC_EACH(__fadd_rn(__fadd_rn(p, __fmul_rn(0.5f, tanhf(a))), q));
+      else PC_EACH(__fadd_rn(p, __fmul_rn(0.5f, tanhf(a))));
+      break;
+    case PCODEC_EPI_CLAMP01: PC_EACH(fminf(fmaxf(a, 0.f), 1.f)); break;
+    default: o = v; break;
+  }
+#undef PC_EACH
   return o;
 }
 
@@ -547,6 +566,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         ok_t |= (__shfl_sync(0xFFFFFFFFu, row_ok ? 1u : 0u, src) & 1u) << i;
       }
       const uint32_t wr_off = (uint32_t)lane * 64u, wr_x = (uint32_t)(lane >> 1) & 3u;
+      if (threadIdx.x == 0) TC_TRACE_G(9);
       for (int c0 = third * 16; c0 < bn; c0 += 16 * (TC_PRODUCER_WARPS / 4)) {
         if (n0 + c0 >= d.cout) break;  // padded last N tile
         float acc[16];
@@ -559,14 +579,16 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] += part[j];
         }
+        if (threadIdx.x == 0 && c0 == 0) TC_TRACE_G(5);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<float4 *>(stg + wr_off + (((uint32_t)q ^ wr_x) << 4)) =
               make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
         __syncwarp();
+        if (threadIdx.x == 0 && c0 == 0) TC_TRACE_G(6);
         const int co = n0 + c0 + 4 * cc;
         const float4 bias4 = d.bias ? __ldg(reinterpret_cast<const float4 *>(d.bias + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = i * 8 + rl;
           const float4 v = *reinterpret_cast<const float4 *>(stg + r * 64 + (((uint32_t)cc ^ ((uint32_t)(r >> 1) & 3u)) << 4));
@@ -578,7 +600,9 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
           const float4 o = tc_epilogue4(d.epilogue, make_float4(v.x + bias4.x, v.y + bias4.y, v.z + bias4.z, v.w + bias4.w),
                                         a1, a2, has_r2);
           *reinterpret_cast<float4 *>(d.out + opix_t[i] * d.out_pixel_stride + co) = o;
+          if (threadIdx.x == 0 && c0 == 0 && i == 0) TC_TRACE_G(7);
         }
+        if (threadIdx.x == 0 && c0 == 0) TC_TRACE_G(8);
         __syncwarp();
       }
     } else {
