@@ -7,7 +7,7 @@ Public surface mirrors the reference:
   * ``pmf_to_quantized_cdf``                                          (compressai._CXX)
 All arithmetic runs in libpcodec_b200.so (C-ABI: include/pcodec_b200.h); there is no CPU fallback.
 """
-from . import _lib, ans, pipeline  # noqa: F401
+from . import _lib, ans, checkpoint, container, evaluation, pipeline  # noqa: F401
 from ._lib import PcodecError, build_library  # noqa: F401
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional, pmf_to_quantized_cdf  # noqa: F401
 from .models import ChannelProgresssiveWACNN, get_scale_table  # noqa: F401

@@ -36,14 +36,14 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                  // fp32 elements per K slab = 128 bytes = one swizzle row
 constexpr int TC_A_BYTES = TC_BM * 128;    // one A tile (hi or lo)
-constexpr int TC_PRODUCER_WARPS = 12;  // 4 loader warps + 2 groups of 4 converter warps
-constexpr int TC_THREADS = 32 * (TC_PRODUCER_WARPS + 2);  // warps 0-11: A producers + epilogue, warp 12: TMA + TMEM alloc, warp 13: MMA issuer
+// warps 0..4+4*NG-1: A producers (4 loaders + NG converter groups) + epilogue; next warp: TMA + TMEM alloc; last: MMA issuer
 constexpr int TC_SMEM_LIMIT = 225 * 1024;
 
 struct TcWeights {
   CUtensorMap map_hi, map_lo;
   float *dev_hi, *dev_lo;  // [cout][k_total]
   int cout, k_total, bn, n_tiles;
+  int small;  // 1: two-CTAs-per-SM variant (short reductions): bn <= 64, <= 256 TMEM columns, <= 3 stages
 };
 
 struct TcParams {
@@ -273,9 +273,15 @@ __device__ long long g_tc_trace[TC_TRACE_SLABS * TC_TRACE_EVENTS + 32];
   do {                                                                                \
     if (trace) g_tc_trace[TC_TRACE_SLABS * TC_TRACE_EVENTS + (ev)] = clock64();        \
   } while (0)
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NG = number of converter groups.  NG = 2 (14 warps, one CTA per SM) is the throughput configuration for long
+// reductions.  NG = 1 (10 warps, <= 102 registers) lets TWO CTAs share an SM when the tile needs <= ~110 KB of
+// shared memory and <= 256 TMEM columns: short reductions spend most of their time in the (serial) prologue and
+// epilogue of a tile, which a second resident CTA overlaps with its own main loop.
+template <int NG>
+__global__ void __launch_bounds__(32 * (4 + 4 * NG + 2), NG == 1 ? 2 : 1)
 conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap map_hi,
                     const __grid_constant__ CUtensorMap map_lo) {
+  constexpr int TC_PRODUCER_WARPS = 4 + 4 * NG;  // 4 loader warps + NG groups of 4 converter warps
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const pcodec_conv_desc &d = P.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -444,7 +450,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
       // Two converter groups (warps 4-7 / 8-11) take alternate K slabs, each with its own A operand buffer: one
       // group's wait -> LDS -> tcgen05.st -> wait::st -> arrive chain (latency bound, ~1 us) overlaps the other's.
       const int grp = (warp - 4) >> 2;
-      for (int s = grp; s < n_steps; s += 2) {
+      for (int s = grp; s < n_steps; s += NG) {
         const int q = s % a_ring;
         const int st = s % stages;
         const uint32_t ph = (uint32_t)(s / stages) & 1u;
@@ -531,8 +537,14 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
           for (int j = 0; j < 16; ++j) acc[j] += part[j];
         }
         if (row_ok) {
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = tc_epilogue(d.epilogue, acc[j] + (d.bias ? __ldg(d.bias + j) : 0.f), 0.f, 0.f, false);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = d.bias ? __ldg(reinterpret_cast<const float4 *>(d.bias) + j4) : z4;
+            const float4 o = tc_epilogue4(d.epilogue, make_float4(acc[4 * j4] + b4.x, acc[4 * j4 + 1] + b4.y,
+                                                                   acc[4 * j4 + 2] + b4.z, acc[4 * j4 + 3] + b4.w), z4, z4, false);
+            acc[4 * j4] = o.x; acc[4 * j4 + 1] = o.y; acc[4 * j4 + 2] = o.z; acc[4 * j4 + 3] = o.w;
+          }
           const int64_t plane = (int64_t)d.out_h * d.out_w;
           for (int c = 0; c < Cimg && c < 4; ++c)
             for (int py = 0; py < 2; ++py) {
@@ -597,8 +609,10 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 a2 = d.r2 ? __ldg(reinterpret_cast<const float4 *>(d.r2 + opix_t[i] * d.r2_pixel_stride + co))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (threadIdx.x == 0 && c0 == 0 && i == 0 && v.x != 123.f) TC_TRACE_G(10);
           const float4 o = tc_epilogue4(d.epilogue, make_float4(v.x + bias4.x, v.y + bias4.y, v.z + bias4.z, v.w + bias4.w),
                                         a1, a2, has_r2);
+          if (threadIdx.x == 0 && c0 == 0 && i == 0 && o.x != 123.f) TC_TRACE_G(11);
           *reinterpret_cast<float4 *>(d.out + opix_t[i] * d.out_pixel_stride + co) = o;
           if (threadIdx.x == 0 && c0 == 0 && i == 0) TC_TRACE_G(7);
         }
@@ -767,9 +781,8 @@ __global__ void split_weights_kernel(const float *__restrict__ w_tap_major, int 
 // accuracy (measured: rms 3e-5 -> 3e-6 at K = 4800 going from 1 to 4 accumulators).  Tiles are multiples of 16 and
 // need not divide cout: the last tile may be padded (TMA zero-fills out-of-range weight rows, the epilogue skips
 // columns >= cout).
-int pick_bn(int cout, int k_total) {
+int pick_bn(int cout, int k_total, int cap = 256, int tmem_cols = 512) {
   if (cout % 16 != 0) return 0;
-  int cap = 256;
   if (const char *e = getenv("PCODEC_TC_BNCAP")) cap = atoi(e);  // experiment knob
   const int n_steps = (k_total + TC_BK - 1) / TC_BK;
   const int need_hi = std::max(1, (4 * n_steps + 319) / 320);
@@ -777,7 +790,7 @@ int pick_bn(int cout, int k_total) {
     int bn = (cout + tiles - 1) / tiles;
     bn = (bn + 15) & ~15;
     if (bn > cap) continue;
-    const int n_acc = (512 - 128) / bn;  // next to two 64-column A operand buffers
+    const int n_acc = (tmem_cols - 128) / bn;  // next to two 64-column A operand buffers
     if (n_acc - 1 >= std::min(need_hi, 4) || bn == 16) return bn;
   }
   return 0;
@@ -789,7 +802,13 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
                                       void *stream) {
   if (!w_tap_major || !handle_out || n_taps < 1 || cin_total < 4 || cout < 1) return PCODEC_ERR_BAD_ARG;
   *handle_out = nullptr;
-  const int bn = pick_bn(cout, n_taps * cin_total);
+  // short reductions (<= 20 K slabs: the 1x1 convolutions, GDN, Linear layers) use the two-CTAs-per-SM variant
+  const int n_slabs = (n_taps * cin_total + TC_BK - 1) / TC_BK;
+  // (measured slower than one wide tile per SM on this model's layers — more N tiles, more A re-reads — so it is
+  // opt-in: PCODEC_TC_SMALL=1)
+  bool small = false;
+  if (const char *e = getenv("PCODEC_TC_SMALL")) small = atoi(e) != 0 && n_taps == 1 && n_slabs <= 20;
+  const int bn = small ? pick_bn(cout, n_taps * cin_total, 64, 256) : pick_bn(cout, n_taps * cin_total);
   if (bn == 0 || (cin_total % 4) != 0) return PCODEC_ERR_UNSUPPORTED;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return PCODEC_ERR_UNSUPPORTED;
@@ -798,6 +817,7 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
   h->k_total = n_taps * cin_total;
   h->bn = bn;
   h->n_tiles = (cout + bn - 1) / bn;
+  h->small = small ? 1 : 0;
   const size_t bytes = sizeof(float) * (size_t)cout * h->k_total;
   if (cudaMalloc(&h->dev_hi, bytes) != cudaSuccess || cudaMalloc(&h->dev_lo, bytes) != cudaSuccess) {
     delete h;
@@ -871,12 +891,14 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   P.n_steps = n_steps;
   const bool split3 = P.split == 3;
   const int stage_bytes = TC_A_BYTES + (split3 ? 2 : 1) * h->bn * 128;  // raw A staging tile | B_hi | (B_lo)
-  auto need = [&](int st) { return std::max(st * stage_bytes, TC_PRODUCER_WARPS * 2048) + 1024 + 8 * (4 * st + 6) + 64; };
+  auto need = [&](int st) { return std::max(st * stage_bytes, 12 * 2048) + 1024 + 8 * (4 * st + 6) + 64; };
+  const int smem_limit = h->small ? 110 * 1024 : TC_SMEM_LIMIT;
+  const int tmem_limit = h->small ? 256 : 512;
   int stages = 2;
-  while (need(stages + 1) <= TC_SMEM_LIMIT && stages < 8) ++stages;
+  while (need(stages + 1) <= smem_limit && stages < 8) ++stages;
   if (const char *e = getenv("PCODEC_TC_STAGES")) stages = std::min(stages, atoi(e));  // experiment knob
   if (stages > n_steps) stages = n_steps;
-  if (stages < 1 || need(stages) > TC_SMEM_LIMIT) return PCODEC_ERR_UNSUPPORTED;
+  if (stages < 1 || need(stages) > smem_limit) return PCODEC_ERR_UNSUPPORTED;
   P.stages = stages;
   P.raw_stages = 0;
   if (const char *e = getenv("PCODEC_TC_DEBUG")) P.raw_stages = atoi(e);  // experiment knob (wrong results!)
@@ -885,15 +907,15 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
     // Prefer a 3-deep A ring; spend what is left on hi accumulators (up to 4).
     const int a_cols = split3 ? 64 : 32;
     const int need_hi = std::min(4, std::max(1, (4 * n_steps + 319) / 320));  // same rule as pick_bn
-    int ring = 3;
-    int n_acc = (512 - ring * a_cols) / h->bn;
+    int ring = h->small ? 2 : 3;
+    int n_acc = (tmem_limit - ring * a_cols) / h->bn;
     if (n_acc - (split3 ? 1 : 0) < need_hi) {  // wide tile: a 2-deep ring rather than too few hi accumulators
       ring = 2;
-      n_acc = (512 - ring * a_cols) / h->bn;
+      n_acc = (tmem_limit - ring * a_cols) / h->bn;
     }
     if (const char *e = getenv("PCODEC_TC_RING")) {  // experiment knob
       ring = std::max(2, std::min(4, atoi(e)));
-      n_acc = (512 - ring * a_cols) / h->bn;
+      n_acc = (tmem_limit - ring * a_cols) / h->bn;
     }
     int n_hi = n_acc - (split3 ? 1 : 0);
     if (n_hi > 4) n_hi = 4;
@@ -905,15 +927,20 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   }
   const int smem = need(stages);
   if (getenv("PCODEC_TC_VERBOSE"))
-    fprintf(stderr, "[conv_tc] M=%lld bn=%d n_tiles=%d n_steps=%d stages=%d n_hi=%d ring=%d split=%d smem=%d\n", (long long)P.M,
-            h->bn, h->n_tiles, n_steps, stages, P.n_hi_acc, P.a_ring, P.split, smem);
+    fprintf(stderr, "[conv_tc] M=%lld bn=%d n_tiles=%d n_steps=%d stages=%d n_hi=%d ring=%d split=%d smem=%d small=%d\n",
+            (long long)P.M, h->bn, h->n_tiles, n_steps, stages, P.n_hi_acc, P.a_ring, P.split, smem, h->small);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    attr_err = cudaFuncSetAttribute(conv_taps_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_taps_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
   });
   if (attr_err != cudaSuccess) return -(int)attr_err;
   dim3 grid((unsigned)ceil_div64(P.M, TC_BM), (unsigned)h->n_tiles);
-  conv_taps_tc_kernel<<<grid, TC_THREADS, smem, as_stream(stream)>>>(P, h->map_hi, h->map_lo);
+  if (h->small)
+    conv_taps_tc_kernel<1><<<grid, 32 * 10, smem, as_stream(stream)>>>(P, h->map_hi, h->map_lo);
+  else
+    conv_taps_tc_kernel<2><<<grid, 32 * 14, smem, as_stream(stream)>>>(P, h->map_hi, h->map_lo);
   PCODEC_RETURN_LAUNCH();
 }

@@ -34,7 +34,7 @@ t0 = g[0]
 print(f"cin {cin} cout {cout} k{k} dbg {dbg} split {split}")
 print("global: setup_done %d  tmem_full %d  epilogue_end %d  exit %d" % tuple(v - t0 for v in g[1:5]))
 names = ["ld_empty", "ld_pub", "cv_top", "cv_rawfull", "cv_aempty", "cv_stdone", "cv_arrived", "mma_top", "mma_afull", "mma_bfull", "mma_commit", "mma_mmas"]
-print("epilogue (rel. tmem_full): setup %d | chunk0: tmem-ld %d  sts %d  pass0 %d  chunk-end %d" % tuple(buf[NS*NE+i] - g[2] for i in (9,5,6,7,8)))
+print("epilogue (rel. tmem_full): setup %d | chunk0: tmem-ld %d  sts %d  pass0[lds %d  math %d  stg %d]  chunk-end %d" % tuple(buf[NS*NE+i] - g[2] for i in (9,5,6,10,11,7,8)))
 print("slab 9 per-MMA issue times (rel. to mma_bfull):", [buf[NS * NE + 5 + i] - buf[9 * NE + 9] for i in range(12)])
 print("slab " + " ".join(f"{n:>10s}" for n in names))
 slabs = k * k * ((cin + 31) // 32)
