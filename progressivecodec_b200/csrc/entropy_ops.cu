@@ -11,6 +11,8 @@
 // coder consumes planes in NCHW order.  Each CTA therefore handles a [32 pixels x 32 channels] tile:
 // coalesced 128 B reads along channels, a padded shared-memory transpose, coalesced 128 B writes along
 // pixels.  Every element is read once and every output written once (24 B/element for the encoder step).
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -31,7 +33,10 @@ __device__ __forceinline__ float key_float(uint32_t k) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 quantile_threshold_kernel(const float *__restrict__ scale, int64_t hw, int channels, int ps, float q,
-                          float *__restrict__ thr) {
+                          float *__restrict__ thr, int cache_keys) {
+  // cache_keys: the n sort keys of the image fit the dynamic shared memory (196 KB for a 32x48x32 slice), so the four
+  // radix passes and the successor search read them from there instead of re-reading sigma from L2 five times
+  extern __shared__ uint32_t s_keys[];
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_digit, s_kk, s_below, s_equal, s_min;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -55,7 +60,14 @@ quantile_threshold_kernel(const float *__restrict__ scale, int64_t hw, int chann
       const int64_t e = e0 + tid;
       int bin = -1;
       if (e < n) {
-        const uint32_t key = float_key(__ldg(img + (e / channels) * ps + (e % channels)));
+        uint32_t key;
+        if (cache_keys && pass > 0) {
+          key = s_keys[e];
+        } else {
+          const uint32_t ee = (uint32_t)e, px = ee / (uint32_t)channels;
+          key = float_key(__ldg(img + (int64_t)px * ps + (ee - px * (uint32_t)channels)));
+          if (cache_keys) s_keys[e] = key;
+        }
         if ((key & pmask) == prefix) bin = (int)((key >> shift) & 255u);
       }
       // warp-aggregated histogram update (sigma keys cluster in a handful of top-digit bins)
@@ -88,7 +100,13 @@ quantile_threshold_kernel(const float *__restrict__ scale, int64_t hw, int chann
     __syncthreads();
     uint32_t best = 0xFFFFFFFFu;
     for (int64_t e = tid; e < n; e += 1024) {
-      const uint32_t key = float_key(__ldg(img + (e / channels) * ps + (e % channels)));
+      uint32_t key;
+      if (cache_keys) {
+        key = s_keys[e];
+      } else {
+        const uint32_t ee = (uint32_t)e, px = ee / (uint32_t)channels;
+        key = float_key(__ldg(img + (int64_t)px * ps + (ee - px * (uint32_t)channels)));
+      }
       if (key > key_lo && key < best) best = key;
     }
     for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, d));
@@ -469,7 +487,18 @@ extern "C" int pcodec_quantile_threshold(const float *scale, int batch, int64_t 
                                          float q, float *thr, uint32_t *workspace, void *stream) {
   (void)workspace;
   if (!scale || !thr || batch <= 0 || hw <= 0 || channels <= 0) return PCODEC_ERR_BAD_ARG;
-  quantile_threshold_kernel<<<batch, 1024, 0, as_stream(stream)>>>(scale, hw, channels, pixel_stride, q, thr);
+  const int64_t n = hw * channels;
+  if (n >= (1ll << 31)) return PCODEC_ERR_UNSUPPORTED;
+  constexpr int kKeyCacheMax = 200 * 1024;  // bytes of dynamic shared memory for the key cache
+  const int cache = n * 4 <= kKeyCacheMax ? 1 : 0;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(quantile_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKeyCacheMax);
+  });
+  if (attr_err != cudaSuccess) return -(int)attr_err;
+  quantile_threshold_kernel<<<batch, 1024, cache ? (size_t)n * 4 : 0, as_stream(stream)>>>(scale, hw, channels,
+                                                                                            pixel_stride, q, thr, cache);
   PCODEC_RETURN_LAUNCH();
 }
 

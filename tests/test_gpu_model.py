@@ -209,3 +209,27 @@ def test_config3_batched_forward_training_crops():
     for l in (0, 5, len(full) - 1):
         fsq = net.forward_single_quality(x.cuda(), full[l], mask_pol=pol, training=False)["x_hat"]
         assert torch.allclose(o13["x_hat"][l].clamp(0, 1), fsq, atol=1e-6), full[l]
+
+
+def test_pipelined_sweep_equals_sequential_calls():
+    """pipeline.sweep (compress(q+1) overlapped with decompress(q) on two threads / streams) returns exactly what the
+    back-to-back calls return, through device streams and through python `bytes`."""
+    from progressivecodec_b200 import pipeline
+
+    net, _ = build_pair("authors", "cuda")
+    x = synthetic_image((3, 3, 128, 192), seed=17).cuda()
+    qs = [0, 0.5, 2, 10]
+    seq = []
+    for q in qs:
+        c = net.compress(x, quality=q)
+        seq.append((c["strings"], net.decompress(c["strings"], c["shape"], quality=q)["x_hat"]))
+    got_dev = pipeline.sweep(net, x, qs)
+    seen = {}
+    got_host = pipeline.sweep(net, x, qs, host_strings=True, on_result=lambda q, c, r: seen.__setitem__(q, c["strings"]))
+    for i, q in enumerate(qs):
+        assert torch.equal(got_dev[i], seq[i][1]), q
+        assert torch.equal(got_host[i], seq[i][1]), q
+        assert seen[q][0] == seq[i][0][0] and seen[q][1] == seq[i][0][1]
+    # errors on the worker thread surface on the caller
+    with pytest.raises(NotImplementedError):
+        pipeline.sweep(net, x, [1], mask_pol="no-such-policy")
