@@ -233,3 +233,49 @@ def test_pipelined_sweep_equals_sequential_calls():
     # errors on the worker thread surface on the caller
     with pytest.raises(NotImplementedError):
         pipeline.sweep(net, x, [1], mask_pol="no-such-policy")
+
+
+def test_streams_are_batch_invariant_and_cross_decodable():
+    """An image's streams do not depend on what else is in the batch (deterministic, batch-invariant kernels), and
+    streams produced in a batch decode alone (and vice versa) to the same picture — what a codec needs in deployment,
+    where the encoder batch and the decoder batch differ."""
+    net, _ = build_pair("authors", "cuda")
+    x = synthetic_image((5, 3, 128, 192), seed=23).cuda()
+    for q in (0, 1.25):
+        cb = net.compress(x, quality=q)
+        rb = net.decompress(cb["strings"], cb["shape"], quality=q)["x_hat"]
+        for i in (0, 3):
+            ci = net.compress(x[i:i + 1], quality=q)
+            assert [s[0] for s in ci["strings"][0]] == [s[i] for s in cb["strings"][0]], (q, i)
+            assert ci["strings"][1][0] == cb["strings"][1][i]
+            single = [[[s[i]] for s in cb["strings"][0]], [cb["strings"][1][i]]]
+            ri = net.decompress(single, cb["shape"], quality=q)["x_hat"]
+            assert torch.equal(ri[0], rb[i]), (q, i)
+
+
+def test_config4_clic_size_per_quality_vs_oracle():
+    """BASELINE config 4 shape (2048x1365 padded to 2048x1408, y = [1,640,88,128]): per-quality compress/decompress
+    against the CPU oracle's own round trip at one mid level — z / first-divergence symbol disagreement <= 1e-4, rate
+    within 0.5 %, PSNR within 0.02 dB."""
+    net, orc = build_pair("authors", "cuda")
+    x = torch.nn.functional.pad(synthetic_image((1, 3, 1365, 2048), seed=6), (0, 0, 21, 22))
+    q = 1
+    dbg, odbg = {}, {}
+    out = net.compress(x.cuda(), quality=q, debug=dbg)
+    o = orc.compress(x, quality=q, debug=odbg)
+    # z: 135 168 symbols; a rounding tie may flip a few of them (<= 1e-4), after which the two sides legitimately see
+    # different hyper latents, so the y planes are compared stage-wise only when z agrees
+    z_bad = float((dbg["z_symbols"].cpu().reshape(odbg["z_sym"].shape) != odbg["z_sym"]).float().mean())
+    assert z_bad <= 1e-4, z_bad
+    if z_bad == 0:
+        sym, idx = dbg["symbols"].cpu(), dbg["indexes"].cpu()
+        for s_ in range(sym.shape[0]):
+            bad = (sym[s_] != odbg["symbols"][s_].reshape(1, -1)) | (idx[s_] != odbg["indexes"][s_].reshape(1, -1))
+            if bad.any():
+                assert float(bad.float().mean()) <= 1e-4, s_
+                break
+    b_gpu, b_ref = _total_bytes(out["strings"]), _total_bytes(o["strings"])
+    assert abs(b_gpu - b_ref) <= 0.005 * b_ref + 8
+    rec = net.decompress(out["strings"], out["shape"], quality=q)["x_hat"].cpu()
+    rec_orc = orc.decompress(o["strings"], tuple(o["shape"]), quality=q)["x_hat"]
+    assert abs(psnr(rec, x) - psnr(rec_orc, x)) <= 0.02
