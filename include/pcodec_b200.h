@@ -146,6 +146,15 @@ int pcodec_slice_quantize(const float *y, int y_ps, const float *y_sub, int y_su
                           int32_t *symbols, int32_t *indexes, float *mask_out, float *lik, float *y_hat, int y_hat_ps,
                           void *stream);
 
+/* pcodec_slice_quantize with a custom importance map (ChannelMask.forward(cust_map=...), masking.py:171-194, reached
+ * from compress/decompress at CHProg_cnn.py:721,823,850,964): in PCODEC_MASK_THRESHOLD mode the mask is
+ * mask_src >= thr[b] instead of scale >= thr[b]; everything else (index from scale*mask, symbol, y_hat) is unchanged. */
+int pcodec_slice_quantize_cust(const float *y, int y_ps, const float *y_sub, int y_sub_ps, const float *mu, int mu_ps,
+                               const float *scale, int scale_ps, int batch, int64_t hw, int channels, int mask_mode,
+                               const float *thr, const float *scale_table, int n_levels, float scale_bound,
+                               int32_t *symbols, int32_t *indexes, float *mask_out, float *lik, float *y_hat,
+                               int y_hat_ps, const float *mask_src, int mask_src_ps, void *stream);
+
 /* Decoder-side: index (and mask) only (CHProg_cnn.py:891, 960-968). */
 int pcodec_slice_indexes(const float *scale, int scale_ps, int batch, int64_t hw, int channels, int mask_mode,
                          const float *thr, const float *scale_table, int n_levels, float scale_bound,

@@ -233,8 +233,19 @@ class OracleCodec:
         return torch.cat([m0, m1], 1), torch.cat([s0, s1], 1)
 
     # -- masking -----------------------------------------------------------------------------
-    def mask(self, scale: Tensor, pr: float, mask_pol: Optional[str]) -> Tensor:
+    def mask(self, scale: Tensor, pr: float, mask_pol: Optional[str], cust_map: Optional[Tensor] = None) -> Tensor:
         """ChannelMask.forward — layers/masking.py:163-226 (policies on the inference path)."""
+        if cust_map is not None:  # masking.py:171-194: the importance map replaces sigma, whatever the policy
+            if pr >= 10:
+                return torch.ones_like(cust_map)
+            if pr == 0:
+                return torch.zeros_like(cust_map)
+            q = 1.0 - pr * 0.1
+            out = torch.zeros_like(cust_map)
+            for j in range(cust_map.shape[0]):
+                flat = cust_map[j].reshape(-1)
+                out[j] = (flat >= torch.quantile(flat, q)).reshape(cust_map.shape[1:]).to(cust_map.dtype)
+            return out
         if mask_pol is None:
             mask_pol = self.cfg.mask_policy
         if mask_pol is None:
@@ -420,7 +431,8 @@ class OracleCodec:
     # compress() — models/CHProg_cnn.py:686-847
     # ==========================================================================================
     @torch.no_grad()
-    def compress(self, x: Tensor, quality=0.0, mask_pol: Optional[str] = None, coder=None, debug: Optional[dict] = None):
+    def compress(self, x: Tensor, quality=0.0, mask_pol: Optional[str] = None, coder=None, debug: Optional[dict] = None,
+                 cust_map: Optional[Tensor] = None):
         c = self.cfg
         coder = coder or EP.default_coder()
         mask_pol = c.mask_policy if mask_pol is None else mask_pol
@@ -472,7 +484,8 @@ class OracleCodec:
             scale = self.slice_net(scale_support, f"cc_scale_transforms_prog.{i}")
             std_total.append(scale if c.support_std else mut)
             mu_total.append(mut)
-            m = self.mask(scale, quality, mask_pol)
+            cm = cust_map.chunk(self.ns1 - self.ns0, 1)[i] if cust_map is not None else None  # CHProg_cnn.py:721
+            m = self.mask(scale, quality, mask_pol, cm)
             masks.append(m)
             m = torch.round(m)
             idx = self.gc.build_indexes(scale * m)
@@ -492,7 +505,8 @@ class OracleCodec:
     # decompress() — models/CHProg_cnn.py:849-999
     # ==========================================================================================
     @torch.no_grad()
-    def decompress(self, strings, shape, quality, mask_pol: Optional[str] = None, coder=None):
+    def decompress(self, strings, shape, quality, mask_pol: Optional[str] = None, coder=None,
+                   cust_map: Optional[Tensor] = None):
         c = self.cfg
         coder = coder or EP.default_coder()
         mask_pol = c.mask_policy if mask_pol is None else mask_pol
@@ -528,7 +542,8 @@ class OracleCodec:
             scale = self.slice_net(scale_support, f"cc_scale_transforms_prog.{i}")
             std_total.append(scale if c.support_std else mut)
             mu_total.append(mut)
-            m = self.mask(scale, quality, mask_pol)
+            cm = cust_map.chunk(self.ns1 - self.ns0, 1)[i] if cust_map is not None else None  # CHProg_cnn.py:850
+            m = self.mask(scale, quality, mask_pol, cm)
             idx = self.gc.build_indexes(scale * m)
             sym = self.gc.decode(y_strings[self.ns0 + i], idx, coder)
             y_hat = sym.float() + mu

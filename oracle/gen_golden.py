@@ -171,6 +171,42 @@ def run_case(name: str, check: bool):
             float(np.abs(o["likelihoods"]["z"].numpy() - rec["fwd_lik_z"]).max())))
 
 
+def run_custmap(check: bool):
+    """cust_map path (masking.py:171-194 via CHProg_cnn.py:721,823,850,964): the importance map replaces sigma in the
+    mask; authors' flags, two levels.  -> tests/golden/authors_custmap.npz"""
+    kwargs, shape = CASES["authors"]
+    net = build_reference(kwargs)
+    x = synthetic_image(shape, seed=77)
+    g = torch.Generator().manual_seed(4242)
+    cmap = torch.rand(shape[0], 320, shape[2] // 16, shape[3] // 16, generator=g)
+    rec = {"x": x.numpy(), "cust_map": cmap.numpy()}
+    qs = [0.5, 5]
+    with torch.no_grad():
+        for q in qs:
+            c = net.compress(x, quality=q, mask_pol="point-based-std", cust_map=cmap)
+            d = net.decompress(c["strings"], c["shape"], quality=q, mask_pol="point-based-std", cust_map=cmap)
+            tag = f"q{q}_"
+            for k, v in pack_strings(c["strings"]).items():
+                rec[tag + k] = v
+            rec[tag + "shape"] = np.array(list(c["shape"]), dtype=np.int64)
+            rec[tag + "x_hat"] = d["x_hat"].numpy()
+            rec[tag + "mask_sum"] = np.array([float(m.sum()) for m in c["masks"]])
+    path = os.path.join(GOLD, "authors_custmap.npz")
+    np.savez_compressed(path, **rec)
+    print(f"[golden] authors_custmap: {os.path.getsize(path) / 1024:.0f} KiB")
+    if check:
+        from .codec_port import CodecConfig, OracleCodec
+
+        orc = OracleCodec(net.state_dict(), CodecConfig(**kwargs))
+        for q in qs:
+            c = orc.compress(x, quality=q, mask_pol="point-based-std", cust_map=cmap)
+            ref = unpack_strings(rec, f"q{q}_")
+            same = c["strings"][0] == ref[0] and c["strings"][1] == ref[1]
+            d = orc.decompress(ref, tuple(rec[f"q{q}_shape"]), quality=q, mask_pol="point-based-std", cust_map=cmap)
+            err = float(np.abs(d["x_hat"].numpy() - rec[f"q{q}_x_hat"]).max())
+            print(f"   custmap q={q}: strings identical={same}, x_hat max|d|={err:.3g}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -178,7 +214,10 @@ def main():
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
     for name in a.cases:
-        run_case(name, a.check)
+        if name == "custmap":
+            run_custmap(a.check)
+        else:
+            run_case(name, a.check)
 
 
 if __name__ == "__main__":

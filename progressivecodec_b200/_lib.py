@@ -68,6 +68,8 @@ PROTOTYPES = {
     "pcodec_quantile_threshold": (_i, [_vp, _i, _i64, _i, _i, _f, _vp, _vp, _vp]),
     "pcodec_slice_quantize": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp, _vp, _i, _f,
                                    _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "pcodec_slice_quantize_cust": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp, _vp, _i, _f,
+                                        _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "pcodec_slice_indexes": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _i, _f, _vp, _vp]),
     "pcodec_slice_dequantize": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _i, _vp]),
     "pcodec_bottleneck_quantize": (_i, [_vp, _i, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _vp]),

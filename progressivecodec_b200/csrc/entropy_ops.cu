@@ -151,6 +151,7 @@ struct QuantArgs {
   const float *thr; const float *table; int n_levels; float bound;
   int32_t *symbols; int32_t *indexes; float *mask_out; float *lik;
   float *y_hat; int y_hat_ps;
+  const float *mask_src; int mask_src_ps;  // cust_map: the mask is mask_src >= thr instead of scale >= thr
 };
 
 // grid: (pixel tiles, channel groups of 32, batch); block (32, 8)
@@ -175,7 +176,8 @@ __global__ void __launch_bounds__(256) slice_quantize_kernel(QuantArgs a) {
       const int64_t pix = (int64_t)b * a.hw + p;
       float s = a.scale ? a.scale[pix * a.scale_ps + c] : 0.f;
       const float mu = a.mu ? a.mu[pix * a.mu_ps + c] : 0.f;
-      m = a.mask_mode == PCODEC_MASK_ONES ? 1.f : (a.mask_mode == PCODEC_MASK_ZEROS ? 0.f : (s >= thr ? 1.f : 0.f));
+      const float ms = a.mask_src ? a.mask_src[pix * a.mask_src_ps + c] : s;
+      m = a.mask_mode == PCODEC_MASK_ONES ? 1.f : (a.mask_mode == PCODEC_MASK_ZEROS ? 0.f : (ms >= thr ? 1.f : 0.f));
       float r = 0.f;
       if (a.y) {
         float v = a.y[pix * a.y_ps + c];
@@ -502,18 +504,29 @@ extern "C" int pcodec_quantile_threshold(const float *scale, int batch, int64_t 
   PCODEC_RETURN_LAUNCH();
 }
 
+extern "C" int pcodec_slice_quantize_cust(const float *y, int y_ps, const float *y_sub, int y_sub_ps, const float *mu,
+                                          int mu_ps, const float *scale, int scale_ps, int batch, int64_t hw, int channels,
+                                          int mask_mode, const float *thr, const float *scale_table, int n_levels,
+                                          float scale_bound, int32_t *symbols, int32_t *indexes, float *mask_out,
+                                          float *lik, float *y_hat, int y_hat_ps, const float *mask_src, int mask_src_ps,
+                                          void *stream) {
+  if (batch <= 0 || hw <= 0 || channels <= 0 || !scale_table || n_levels < 1 || n_levels > 4096)
+    return PCODEC_ERR_BAD_ARG;
+  if (mask_mode == PCODEC_MASK_THRESHOLD && (!thr || (!scale && !mask_src))) return PCODEC_ERR_BAD_ARG;
+  QuantArgs a{y, y_ps, y_sub, y_sub_ps, mu, mu_ps, scale, scale_ps, hw, channels, mask_mode, thr, scale_table,
+              n_levels, scale_bound, symbols, indexes, mask_out, lik, y_hat, y_hat_ps, mask_src, mask_src_ps};
+  slice_quantize_kernel<<<tile_grid(hw, channels, batch), dim3(32, 8), sizeof(float) * n_levels, as_stream(stream)>>>(a);
+  PCODEC_RETURN_LAUNCH();
+}
+
 extern "C" int pcodec_slice_quantize(const float *y, int y_ps, const float *y_sub, int y_sub_ps, const float *mu,
                                      int mu_ps, const float *scale, int scale_ps, int batch, int64_t hw, int channels,
                                      int mask_mode, const float *thr, const float *scale_table, int n_levels,
                                      float scale_bound, int32_t *symbols, int32_t *indexes, float *mask_out, float *lik,
                                      float *y_hat, int y_hat_ps, void *stream) {
-  if (batch <= 0 || hw <= 0 || channels <= 0 || !scale_table || n_levels < 1 || n_levels > 4096)
-    return PCODEC_ERR_BAD_ARG;
-  if (mask_mode == PCODEC_MASK_THRESHOLD && (!thr || !scale)) return PCODEC_ERR_BAD_ARG;
-  QuantArgs a{y, y_ps, y_sub, y_sub_ps, mu, mu_ps, scale, scale_ps, hw, channels, mask_mode, thr, scale_table,
-              n_levels, scale_bound, symbols, indexes, mask_out, lik, y_hat, y_hat_ps};
-  slice_quantize_kernel<<<tile_grid(hw, channels, batch), dim3(32, 8), sizeof(float) * n_levels, as_stream(stream)>>>(a);
-  PCODEC_RETURN_LAUNCH();
+  return pcodec_slice_quantize_cust(y, y_ps, y_sub, y_sub_ps, mu, mu_ps, scale, scale_ps, batch, hw, channels, mask_mode, thr,
+                                    scale_table, n_levels, scale_bound, symbols, indexes, mask_out, lik, y_hat, y_hat_ps,
+                                    nullptr, 0, stream);
 }
 
 extern "C" int pcodec_slice_indexes(const float *scale, int scale_ps, int batch, int64_t hw, int channels,

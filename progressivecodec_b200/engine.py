@@ -466,14 +466,15 @@ class Engine:
     def slice_quantize(self, y: Optional[Act], y_sub: Optional[Act], mu: Optional[Act], scale: Act, mask_mode: int,
                        thr: Optional[Tensor], table: Tensor, bound: float, symbols: Optional[Tensor],
                        indexes: Optional[Tensor], mask_out: Optional[Tensor], lik: Optional[Tensor],
-                       y_hat: Optional[Act]) -> None:
+                       y_hat: Optional[Act], mask_src: Optional[Act] = None) -> None:
         p = lambda t: t.data_ptr() if t is not None else None
         ap = lambda a: a.ptr if a is not None else None
         aps = lambda a: a.ps if a is not None else 0
-        L.check(self.lib.pcodec_slice_quantize(ap(y), aps(y), ap(y_sub), aps(y_sub), ap(mu), aps(mu), scale.ptr,
-                                               scale.ps, scale.B, scale.H * scale.W, scale.C, mask_mode, p(thr),
-                                               table.data_ptr(), table.numel(), bound, p(symbols), p(indexes),
-                                               p(mask_out), p(lik), ap(y_hat), aps(y_hat), self.stream()), "slice_quantize")
+        L.check(self.lib.pcodec_slice_quantize_cust(ap(y), aps(y), ap(y_sub), aps(y_sub), ap(mu), aps(mu), scale.ptr,
+                                                    scale.ps, scale.B, scale.H * scale.W, scale.C, mask_mode, p(thr),
+                                                    table.data_ptr(), table.numel(), bound, p(symbols), p(indexes),
+                                                    p(mask_out), p(lik), ap(y_hat), aps(y_hat), ap(mask_src), aps(mask_src),
+                                                    self.stream()), "slice_quantize")
 
     def layer_partition(self, scale: Act, thresholds: Tensor, in_a: Optional[Tensor], in_b: Optional[Tensor],
                         out_a: Optional[Tensor], out_b: Optional[Tensor], counts: Optional[Tensor],

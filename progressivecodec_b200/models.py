@@ -460,7 +460,8 @@ class ChannelProgresssiveWACNN(nn.Module):
         return y_hat_base
 
     def _prog_slices(self, P, lm: Act, ls: Act, y_hat_base: Act, quality, mask_pol, code, mode: str,
-                     state: Optional[dict] = None, residual_before_lrp: bool = False, deferred: Optional[list] = None):
+                     state: Optional[dict] = None, residual_before_lrp: bool = False, deferred: Optional[list] = None,
+                     cust_map: Optional[Act] = None):
         """Progressive loop (CHProg_cnn.py:576-642 / 775-845 / 921-983 / 1091-1166).
         `code(i, mu, scale, mask_mode, thr, y_pre)`; `mode` in {"forward","fsq","codec"} selects the
         mu_total / std_total bookkeeping of that entry point (only observable with all_scalable)."""
@@ -476,7 +477,8 @@ class ChannelProgresssiveWACNN(nn.Module):
         if self.all_scalable:  # per-pass pools so that consecutive list entries are adjacent channel ranges
             mu_pool = E.act(B, h, w, 32 * n_prog)
             sc_pool = E.act(B, h, w, 32 * n_prog)
-        kind, q = ChannelMask.mode_for(mask_pol, quality)
+        # a custom importance map replaces sigma in the mask whatever the policy (masking.py:171-194)
+        kind, q = ChannelMask.mode_for("point-based-std" if cust_map is not None else mask_pol, quality)
         mask_mode = {"ones": L.MASK_ONES, "zeros": L.MASK_ZEROS, "threshold": L.MASK_THRESHOLD}[kind]
         sps = self.support_progressive_slices
         for i in range(n_prog):
@@ -512,9 +514,13 @@ class ChannelProgresssiveWACNN(nn.Module):
                 else:
                     std_total.append(scale if self.support_std else mut)
                     mu_total.append(mut)
-            thr = E.quantile_threshold(scale, q) if mask_mode == L.MASK_THRESHOLD else None
+            cm_i = cust_map.slice(32 * i, 32) if cust_map is not None else None  # cust_map.chunk(10, 1)[i], CHProg_cnn.py:721
+            thr = E.quantile_threshold(cm_i if cm_i is not None else scale, q) if mask_mode == L.MASK_THRESHOLD else None
             y_pre = E.act(B, h, w, 32)
-            code(i, mu, scale, mask_mode, thr, y_pre)
+            if cm_i is not None:
+                code(i, mu, scale, mask_mode, thr, y_pre, mask_src=cm_i)
+            else:
+                code(i, mu, scale, mask_mode, thr, y_pre)
             out_i = y_hat_q.slice(32 * i, 32)
             if residual_before_lrp:  # forward_single_quality only (CHProg_cnn.py:1153-1164)
                 y_pre = Act((y_pre.dense() + base_i.dense()).contiguous())
@@ -668,8 +674,6 @@ class ChannelProgresssiveWACNN(nn.Module):
                  debug: Optional[dict] = None):
         """CHProg_cnn.py:686-847.  One batched rANS launch codes every (slice, image) stream.
         `debug` (tests only) receives the device symbol / index planes [n_slices, B, 32*h*w] and z symbols."""
-        if cust_map is not None:
-            raise NotImplementedError("cust_map (gradient-derived custom masks) is outside the hot path (SURVEY.md §8f)")
         mask_pol = self.mask_policy if mask_pol is None else mask_pol
         x = self._check_input(x)
         P = self.prepare()
@@ -689,14 +693,15 @@ class ChannelProgresssiveWACNN(nn.Module):
         y_hat_base = self._base_slices(P, lm, ls, code_base)
         masks: List[Tensor] = []
         if quality > 0:
-            def code_prog(i, mu, scale, mask_mode, thr, y_pre):
+            def code_prog(i, mu, scale, mask_mode, thr, y_pre, mask_src=None):
                 m = torch.empty((B, 32, h, w), dtype=torch.float32, device=E.device)
                 y_sub = y.slice(32 * i, 32) if self.delta_encode else None
                 E.slice_quantize(y.slice(32 * (self.ns0 + i), 32), y_sub, mu, scale, mask_mode, thr, table, bound,
-                                 sym[self.ns0 + i], idx[self.ns0 + i], m, None, y_pre)
+                                 sym[self.ns0 + i], idx[self.ns0 + i], m, None, y_pre, mask_src=mask_src)
                 masks.append(m)
 
-            self._prog_slices(P, lm, ls, y_hat_base, quality, mask_pol, code_prog, "codec")
+            self._prog_slices(P, lm, ls, y_hat_base, quality, mask_pol, code_prog, "codec",
+                              cust_map=self._cust_map_act(E, cust_map, B, h, w))
         if debug is not None:
             debug.update(symbols=sym, indexes=idx, z_symbols=z_sym, y=E.to_nchw(y), y_hat_base=E.to_nchw(y_hat_base))
         z_data, z_off = _ans.encode_batch(z_sym, z_idx, P["eb_tables"])
@@ -716,8 +721,6 @@ class ChannelProgresssiveWACNN(nn.Module):
         rANS stream is a serial state chain, so a batch is decoded as `decode_groups` image groups, each on its
         own CUDA stream (one host thread per group): while one group's streams are being entropy-decoded by a
         handful of warps, the tensor cores run another group's parameter networks."""
-        if cust_map is not None:
-            raise NotImplementedError("cust_map is outside the hot path (SURVEY.md §8f)")
         mask_pol = self.mask_policy if mask_pol is None else mask_pol
         P = self.prepare()
         E: Engine = P["eng"]
@@ -736,7 +739,7 @@ class ChannelProgresssiveWACNN(nn.Module):
         if groups == 1:
             # slot 1, not 0: slot 0 belongs to the encoder-side entry points, which pipeline.sweep() runs concurrently
             return {"x_hat": self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, 0, B, shape, quality,
-                                                    mask_pol, slot=1)}
+                                                    mask_pol, slot=1, cust_map=cust_map)}
         import threading
 
         from .sharding import shard_bounds
@@ -756,7 +759,8 @@ class ChannelProgresssiveWACNN(nn.Module):
                 st.wait_stream(cur)
                 with torch.cuda.device(dev), torch.cuda.stream(st), torch.no_grad():
                     outs[g] = self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, lo, hi, shape,
-                                                     quality, mask_pol, slot=g + 1)
+                                                     quality, mask_pol, slot=g + 1,
+                                                     cust_map=cust_map[lo:hi] if cust_map is not None else None)
             except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
                 errs[g] = e
 
@@ -792,9 +796,10 @@ class ChannelProgresssiveWACNN(nn.Module):
         table, bound = P["scale_table"], P["scale_bound"]
         tables = P["gc_tables"]
 
-        def decode_slice(s, scale, mask_mode, thr, mu, y_pre):
+        def decode_slice(s, scale, mask_mode, thr, mu, y_pre, mask_src=None):
             ind = torch.empty((B, n), dtype=torch.int32, device=dev)
-            E.slice_quantize(None, None, None, scale, mask_mode, thr, table, bound, None, ind, None, None, None)
+            E.slice_quantize(None, None, None, scale, mask_mode, thr, table, bound, None, ind, None, None, None,
+                             mask_src=mask_src)
             sy = _ans.decode_batch(y_data, y_off_dev[s * B_total + lo:s * B_total + hi + 1], ind, tables)
             E.slice_dequantize(sy, mu, y_pre)
 
@@ -815,15 +820,28 @@ class ChannelProgresssiveWACNN(nn.Module):
             code_many=decode_many if self.batch_independent_slices else None)
         return lm, ls, y_hat_base, decode_slice
 
+    def _cust_map_act(self, E: Engine, cust_map, B: int, h: int, w: int) -> Optional[Act]:
+        """cust_map [B, 32*n_prog, h, w] (NCHW, as the reference takes it) -> NHWC activation of the current call."""
+        if cust_map is None:
+            return None
+        n_prog = self.ns1 - self.ns0
+        if tuple(cust_map.shape) != (B, 32 * n_prog, h, w):
+            raise ValueError(f"cust_map must have shape {(B, 32 * n_prog, h, w)}, got {tuple(cust_map.shape)}")
+        if not cust_map.is_cuda:
+            raise L.PcodecError("cust_map must be a CUDA tensor")
+        return E.from_nchw(cust_map)
+
     def _decompress_group(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, quality, mask_pol,
-                          slot: int = 0):
+                          slot: int = 0, cust_map=None):
         """Decode images [lo, hi) of a batch whose streams are laid out slice-major: stream (s, b) = s*B_total + b."""
         lm, ls, y_hat_base, decode_slice = self._decode_base(P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi,
                                                              shape, enhanced=not (quality == 0), slot=slot)
         if quality == 0:
             return self._g_s(P, y_hat_base, 0, clamp=True)
+        E = P["eng"]
         y_hat_q = self._prog_slices(
             P, lm, ls, y_hat_base, quality, mask_pol,
-            lambda i, mu, scale, mask_mode, thr, y_pre: decode_slice(self.ns0 + i, scale, mask_mode, thr, mu, y_pre),
-            "codec")
+            lambda i, mu, scale, mask_mode, thr, y_pre, mask_src=None: decode_slice(self.ns0 + i, scale, mask_mode, thr, mu,
+                                                                                    y_pre, mask_src),
+            "codec", cust_map=self._cust_map_act(E, cust_map, lm.B, lm.H, lm.W))
         return self._g_s(P, y_hat_q, 1, clamp=True)

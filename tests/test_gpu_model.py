@@ -279,3 +279,32 @@ def test_config4_clic_size_per_quality_vs_oracle():
     rec = net.decompress(out["strings"], out["shape"], quality=q)["x_hat"].cpu()
     rec_orc = orc.decompress(o["strings"], tuple(o["shape"]), quality=q)["x_hat"]
     assert abs(psnr(rec, x) - psnr(rec_orc, x)) <= 0.02
+
+
+def test_cust_map_masks_vs_golden_and_oracle():
+    """compress/decompress with a custom importance map (masking.py:171-194): the mask comes from the map's quantile
+    instead of sigma's.  Masks match the real reference's counts, symbols/indexes agree with the oracle stage-wise,
+    PSNR within 0.02 dB of the reference's reconstruction; a batch (decode groups) gives the same result per image."""
+    net, orc = build_pair("authors", "cuda")
+    G = load_golden("authors_custmap")
+    x, cm = torch.from_numpy(G["x"]), torch.from_numpy(G["cust_map"])
+    for q in (0.5, 5):
+        dbg, odbg = {}, {}
+        out = net.compress(x.cuda(), quality=q, mask_pol="point-based-std", cust_map=cm.cuda(), debug=dbg)
+        got = np.array([float(m.sum()) for m in out["masks"]])
+        assert np.abs(got - G[f"q{q}_mask_sum"]).max() == 0  # the map is an input: the masks must agree exactly
+        orc.compress(x, quality=q, mask_pol="point-based-std", cust_map=cm, debug=odbg)
+        sym, idx = dbg["symbols"].cpu(), dbg["indexes"].cpu()
+        for s in range(sym.shape[0]):
+            bad = (sym[s] != odbg["symbols"][s].reshape(1, -1)) | (idx[s] != odbg["indexes"][s].reshape(1, -1))
+            if bad.any():
+                assert float(bad.float().mean()) * sym.shape[2] <= 1.5, (q, s)
+                break
+        rec = net.decompress(out["strings"], out["shape"], quality=q, mask_pol="point-based-std", cust_map=cm.cuda())["x_hat"]
+        assert abs(psnr(rec.cpu(), x) - psnr(torch.from_numpy(G[f"q{q}_x_hat"]), x)) <= 0.02
+        # batch of 9 copies -> decode groups on separate streams get their own slice of the map
+        xb, cb = x.repeat(9, 1, 1, 1).cuda(), cm.repeat(9, 1, 1, 1).cuda()
+        ob = net.compress(xb, quality=q, mask_pol="point-based-std", cust_map=cb)
+        rb = net.decompress(ob["strings"], ob["shape"], quality=q, mask_pol="point-based-std", cust_map=cb)["x_hat"]
+        for i in (0, 4, 8):
+            assert torch.equal(rb[i], rec[0])

@@ -96,3 +96,22 @@ def test_quantile_restatement_matches_torch():
     m = EP.point_based_std_mask_np(s.numpy(), 2.5)
     ref = torch.stack([(s[b] >= torch.quantile(s[b].reshape(-1), 0.75)).float() for b in range(2)])
     assert np.array_equal(m, ref.numpy())
+
+
+def test_cust_map_masks_match_reference():
+    """cust_map path (masking.py:171-194 via CHProg_cnn.py:721,823,850,964): oracle vs the real reference's streams and
+    reconstruction (tests/golden/authors_custmap.npz, oracle/gen_golden.py --cases custmap)."""
+    _net, orc = build_pair("authors")
+    G = load_golden("authors_custmap")
+    x, cm = torch.from_numpy(G["x"]), torch.from_numpy(G["cust_map"])
+    npx = x.shape[0] * x.shape[2] * x.shape[3]
+    for q in (0.5, 5):
+        ref = unpack_strings(G, f"q{q}_")
+        out = orc.compress(x, quality=q, mask_pol="point-based-std", cust_map=cm)
+        assert np.abs(np.array([float(m.sum()) for m in out["masks"]]) - G[f"q{q}_mask_sum"]).max() == 0
+        if out["strings"][0] != ref[0] or out["strings"][1] != ref[1]:
+            assert abs(bpp_from_strings(out["strings"], npx) - bpp_from_strings(ref, npx)) <= 0.005 * bpp_from_strings(ref, npx)
+        rec = orc.decompress(ref, tuple(G[f"q{q}_shape"]), quality=q, mask_pol="point-based-std", cust_map=cm)["x_hat"]
+        ref_x = torch.from_numpy(G[f"q{q}_x_hat"])
+        if not torch.equal(rec, ref_x):
+            assert abs(psnr(rec, x) - psnr(ref_x, x)) <= 0.02
