@@ -714,8 +714,11 @@ class ChannelProgresssiveWACNN(nn.Module):
         return {"strings": [y_strings, _ans.split_streams(z_data, z_off)], "shape": shape, "masks": masks}
 
     @torch.no_grad()
-    def decompress(self, strings, shape, quality, mask_pol=None, cust_map=None):
+    def decompress(self, strings, shape, quality, mask_pol=None, cust_map=None, _worker: int = 0):
         """CHProg_cnn.py:849-999.
+
+        `_worker` (not part of the reference API) gives concurrent decompress() calls from different host threads their
+        own engine contexts and streams (pipeline.sweep with several decode workers).
 
         The decoder is a strictly serial chain per image (slice i's sigma needs the decoded slice i-1), and one
         rANS stream is a serial state chain, so a batch is decoded as `decode_groups` image groups, each on its
@@ -739,27 +742,30 @@ class ChannelProgresssiveWACNN(nn.Module):
         if groups == 1:
             # slot 1, not 0: slot 0 belongs to the encoder-side entry points, which pipeline.sweep() runs concurrently
             return {"x_hat": self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, 0, B, shape, quality,
-                                                    mask_pol, slot=1, cust_map=cust_map)}
+                                                    mask_pol, slot=1 + 8 * _worker, cust_map=cust_map)}
         import threading
 
         from .sharding import shard_bounds
 
         cur = torch.cuda.current_stream(dev)
-        if self._streams is None or len(self._streams) < groups:
+        if self._streams is None:
+            self._streams = {}
+        if len(self._streams.get(_worker, ())) < groups:
             # high priority: a group's entropy-decode launch is a handful of CTAs on its critical path; it should get
             # the next free SM ahead of the wide convolution grids of other groups / of a concurrent compress()
-            self._streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(groups)]
+            self._streams[_worker] = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(groups)]
+        streams = self._streams[_worker]
         outs: List[Optional[Tensor]] = [None] * groups
         errs: List[Optional[BaseException]] = [None] * groups
 
         def work(g):
             try:
                 lo, hi = shard_bounds(B, g, groups)
-                st = self._streams[g]
+                st = streams[g]
                 st.wait_stream(cur)
                 with torch.cuda.device(dev), torch.cuda.stream(st), torch.no_grad():
                     outs[g] = self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, lo, hi, shape,
-                                                     quality, mask_pol, slot=g + 1,
+                                                     quality, mask_pol, slot=g + 1 + 8 * _worker,
                                                      cust_map=cust_map[lo:hi] if cust_map is not None else None)
             except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
                 errs[g] = e
@@ -773,7 +779,7 @@ class ChannelProgresssiveWACNN(nn.Module):
             if e is not None:
                 raise e
         for g in range(groups):
-            cur.wait_stream(self._streams[g])
+            cur.wait_stream(streams[g])
             outs[g].record_stream(cur)
         return {"x_hat": torch.cat(outs, 0)}
 

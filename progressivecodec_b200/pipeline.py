@@ -17,32 +17,39 @@ import torch
 
 
 def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[str] = None, host_strings: bool = False,
-          on_result: Optional[Callable[[float, dict, dict], None]] = None, keep: bool = True) -> List[Optional[torch.Tensor]]:
+          on_result: Optional[Callable[[float, dict, dict], None]] = None, keep: bool = True,
+          decode_workers: Optional[int] = None) -> List[Optional[torch.Tensor]]:
     """compress + decompress `x` at every level of `qualities`; returns the reconstructions (``x_hat`` per level).
 
     host_strings=False keeps the rANS streams on the device between the two stages (compress(...,
     return_device_streams=True)); host_strings=True goes through python ``bytes`` exactly like the reference API.
-    on_result(q, compressed, decompressed) is called on the worker thread after each level (its stream is
-    synchronised at that point)."""
+    on_result(q, compressed, decompressed) is called on a worker thread after each level (its stream is
+    synchronised at that point).  decode_workers: decompress() calls of different levels are independent too, so small
+    batches (whose 16-phase decode chain leaves the GPU almost idle) run several of them concurrently; default
+    max(1, min(4, 8 // batch))."""
     dev = x.device
     caller_stream = torch.cuda.current_stream(dev)
     enc_stream = torch.cuda.Stream(device=dev)
-    dec_stream = torch.cuda.Stream(device=dev)
+    n_workers = decode_workers if decode_workers else max(1, min(4, 8 // max(1, x.shape[0])))
+    n_workers = max(1, min(4, n_workers))  # decompress() reserves 8 engine slots per worker
+    dec_streams = [torch.cuda.Stream(device=dev) for _ in range(n_workers)]
     enc_stream.wait_stream(caller_stream)
-    q_items: "queue.Queue" = queue.Queue(maxsize=2)
+    q_items: "queue.Queue" = queue.Queue(maxsize=n_workers + 1)
     outs: List[Optional[torch.Tensor]] = [None] * len(qualities)
     err: List[BaseException] = []
 
-    def consumer():
+    def consumer(k: int):
+        dec_stream = dec_streams[k]
         try:
             with torch.cuda.device(dev), torch.cuda.stream(dec_stream), torch.no_grad():
                 while True:
                     item = q_items.get()
                     if item is None:
+                        q_items.put(None)  # pass the end marker on to the other workers
                         return
                     i, q, c = item
                     src = c["strings"] if host_strings else c
-                    r = net.decompress(src, c["shape"], quality=q, mask_pol=mask_pol)
+                    r = net.decompress(src, c["shape"], quality=q, mask_pol=mask_pol, _worker=k)
                     dec_stream.synchronize()  # `c` may be released (and its memory reused by the encoder stream) now
                     if on_result is not None:
                         on_result(q, c, r)
@@ -52,9 +59,11 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
             err.append(e)
             while q_items.get() is not None:  # drain so the producer never blocks on a dead consumer
                 pass
+            q_items.put(None)
 
-    t = threading.Thread(target=consumer, name="pcodec-decompress")
-    t.start()
+    workers = [threading.Thread(target=consumer, args=(k,), name=f"pcodec-decompress-{k}") for k in range(n_workers)]
+    for t in workers:
+        t.start()
     try:
         with torch.cuda.stream(enc_stream), torch.no_grad():
             for i, q in enumerate(qualities):
@@ -65,9 +74,11 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
                 q_items.put((i, q, c))
     finally:
         q_items.put(None)
-        t.join()
+        for t in workers:
+            t.join()
     caller_stream.wait_stream(enc_stream)
-    caller_stream.wait_stream(dec_stream)
+    for st in dec_streams:
+        caller_stream.wait_stream(st)
     if err:
         raise err[0]
     return outs

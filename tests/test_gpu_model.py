@@ -308,3 +308,20 @@ def test_cust_map_masks_vs_golden_and_oracle():
         rb = net.decompress(ob["strings"], ob["shape"], quality=q, mask_pol="point-based-std", cust_map=cb)["x_hat"]
         for i in (0, 4, 8):
             assert torch.equal(rb[i], rec[0])
+
+
+def test_pipelined_sweep_with_several_decode_workers():
+    """Small batches decode several quality levels concurrently (one engine context / stream set per worker)."""
+    from progressivecodec_b200 import pipeline
+
+    net, _ = build_pair("authors", "cuda")
+    x = synthetic_image((1, 3, 128, 192), seed=19).cuda()
+    qs = [0, 0.05, 0.5, 1.25, 5, 10]
+    ref = []
+    for q in qs:
+        c = net.compress(x, quality=q)
+        ref.append(net.decompress(c["strings"], c["shape"], quality=q)["x_hat"])
+    for workers in (None, 3):
+        got = pipeline.sweep(net, x, qs, decode_workers=workers)
+        for i in range(len(qs)):
+            assert torch.equal(got[i], ref[i]), (workers, qs[i])
