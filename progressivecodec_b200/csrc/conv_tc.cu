@@ -53,6 +53,8 @@ struct TcParams {
   int raw_stages;  // debug knob bits (PCODEC_TC_DEBUG): 1 = skip A global loads, 2 = skip B TMA loads, 4 = skip converter TMEM stores
   int n_hi_acc;  // TMEM accumulators for the hi*hi products (round-robin over K slabs); +1 for the lo terms when split
   int a_ring;    // depth of the A operand ring in tensor memory (2..4)
+  uint32_t magic_w, magic_h;  // division by grid_w / grid_h as one multiply (dividends < 2^31): q = (m * magic) >> (31 + shift)
+  int shift_w, shift_h;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -80,6 +82,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity), "r"(0x989680)
       : "memory");
+}
+// exact m / d for m < 2^31 with magic = ceil(2^(31+shift) / d), shift = ceil(log2 d)  (Granlund-Montgomery, N = 31):
+// the tile's pixel coordinates cost 2 multiplies per row instead of 2 integer divisions (~40 instructions each), which
+// was ~2 us of every tile's prologue
+__device__ __forceinline__ uint32_t fast_div(uint32_t m, uint32_t magic, int shift) {
+  return (uint32_t)(((uint64_t)m * magic) >> (31 + shift));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -371,10 +379,11 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     const int prow = threadIdx.x & 127, psub = threadIdx.x >> 7;  // 3 threads per tile row
     const int64_t pm = m0 + prow;
     if (pm < P.M) {
-      const uint32_t pt = (uint32_t)pm / (uint32_t)d.grid_w;
-      const int pw = (int)((uint32_t)pm % (uint32_t)d.grid_w);
-      const int ph_ = (int)(pt % (uint32_t)d.grid_h);
-      const int64_t pn = (int64_t)(pt / (uint32_t)d.grid_h);
+      const uint32_t pt = fast_div((uint32_t)pm, P.magic_w, P.shift_w);
+      const int pw = (int)((uint32_t)pm - pt * (uint32_t)d.grid_w);
+      const uint32_t pnn = fast_div(pt, P.magic_h, P.shift_h);
+      const int ph_ = (int)(pt - pnn * (uint32_t)d.grid_h);
+      const int64_t pn = (int64_t)pnn;
       const int64_t ppix = (pn * d.out_h + (ph_ * d.out_step + d.out_off_y)) * (int64_t)d.out_w + (pw * d.out_step + d.out_off_x);
       for (int c = psub * 32; c < bn && n0 + c < d.cout; c += 32 * (TC_PRODUCER_WARPS / 4)) {
         if (d.r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r1 + ppix * d.r1_pixel_stride + n0 + c));
@@ -399,10 +408,10 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         const int64_t m = m0 + r;
         const bool okr = m < P.M;
         const uint32_t mm = okr ? (uint32_t)m : 0u;  // M < 2^31 (checked on the host): 32-bit divisions
-        const int w = (int)(mm % (uint32_t)d.grid_w);
-        const uint32_t t = mm / (uint32_t)d.grid_w;
-        const int h = (int)(t % (uint32_t)d.grid_h);
-        const int n = (int)(t / (uint32_t)d.grid_h);
+        const uint32_t t = fast_div(mm, P.magic_w, P.shift_w);
+        const int w = (int)(mm - t * (uint32_t)d.grid_w);
+        const int n = (int)fast_div(t, P.magic_h, P.shift_h);
+        const int h = (int)(t - (uint32_t)n * (uint32_t)d.grid_h);
         ih0[i] = okr ? h * d.in_step : -(1 << 28);
         iw0[i] = w * d.in_step;
         pix0[i] = (n * d.in_h + h * d.in_step) * d.in_w + w * d.in_step;
@@ -507,10 +516,11 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     const int64_t m = m0 + row;
     const bool row_ok = m < P.M;
     const int64_t mm = row_ok ? m : 0;
-    const uint32_t mt = (uint32_t)mm / (uint32_t)d.grid_w;
-    const int w = (int)((uint32_t)mm % (uint32_t)d.grid_w);
-    const int h = (int)(mt % (uint32_t)d.grid_h);
-    const int64_t n = (int64_t)(mt / (uint32_t)d.grid_h);
+    const uint32_t mt = fast_div((uint32_t)mm, P.magic_w, P.shift_w);
+    const int w = (int)((uint32_t)mm - mt * (uint32_t)d.grid_w);
+    const uint32_t nn_ = fast_div(mt, P.magic_h, P.shift_h);
+    const int h = (int)(mt - nn_ * (uint32_t)d.grid_h);
+    const int64_t n = (int64_t)nn_;
     const int oh = h * d.out_step + d.out_off_y, ow = w * d.out_step + d.out_off_x;
     const int64_t opix = (n * d.out_h + oh) * (int64_t)d.out_w + ow;
     const bool shuffle = (d.flags & PCODEC_FLAG_PIXEL_SHUFFLE2) != 0;
@@ -884,6 +894,13 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   P.d = *desc;
   P.M = (int64_t)desc->batch * desc->grid_h * desc->grid_w;
   if (P.M >= (1ll << 31) - TC_BM) return PCODEC_ERR_UNSUPPORTED;  // 32-bit pixel arithmetic in the kernel
+  auto magic_for = [](uint32_t dv, uint32_t &magic, int &shift) {
+    shift = 0;
+    while ((1u << shift) < dv) ++shift;
+    magic = (uint32_t)((((uint64_t)1 << (31 + shift)) + dv - 1) / dv);
+  };
+  magic_for((uint32_t)desc->grid_w, P.magic_w, P.shift_w);
+  magic_for((uint32_t)desc->grid_h, P.magic_h, P.shift_h);
   P.bn = h->bn;
   P.split = desc->tc_split;
   int n_steps = 0;
