@@ -814,10 +814,14 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
   *handle_out = nullptr;
   // short reductions (<= 20 K slabs: the 1x1 convolutions, GDN, Linear layers) use the two-CTAs-per-SM variant
   const int n_slabs = (n_taps * cin_total + TC_BK - 1) / TC_BK;
-  // (measured slower than one wide tile per SM on this model's layers — more N tiles, more A re-reads — so it is
-  // opt-in: PCODEC_TC_SMALL=1)
+  // Opt-in only (PCODEC_TC_SMALL=1: cout <= 64; =2: also every 1-tap reduction of <= 20 slabs): on this model it measured
+  // equal or slower than one CTA per SM — for 192-wide 1x1 layers it needs more N tiles (more A re-reads), and for the
+  // narrow slice-stack layers two resident CTAs did not raise the per-SM throughput.
   bool small = false;
-  if (const char *e = getenv("PCODEC_TC_SMALL")) small = atoi(e) != 0 && n_taps == 1 && n_slabs <= 20;
+  if (const char *e = getenv("PCODEC_TC_SMALL")) {
+    const int v = atoi(e);
+    small = (v >= 1 && cout <= 64) || (v >= 2 && n_taps == 1 && n_slabs <= 20);
+  }
   const int bn = small ? pick_bn(cout, n_taps * cin_total, 64, 256) : pick_bn(cout, n_taps * cin_total);
   if (bn == 0 || (cin_total % 4) != 0) return PCODEC_ERR_UNSUPPORTED;
   EncodeTiledFn enc = get_encode_fn();
