@@ -18,6 +18,9 @@
  *   entropy_models/entropy_models.py:400-433, 446-522 EntropyBottleneck           -> pcodec_bottleneck_*
  *   models/utils.py:186-204, layers/layers.py:15-29, layers/gdn.py:50-63          -> pcodec_conv_taps
  *   layers/win_attention.py:84-115,153-207    shifted-window attention core       -> pcodec_window_attention
+ *   layers/masking.py:171-194 (cust_map)      custom importance-map masks          -> pcodec_slice_quantize_cust
+ *   (no reference equivalent) truncatable progressive container                   -> pcodec_layer_partition,
+ *                                                                                    pcodec_rans_encode_segments / _decode_segments
  *
  * Activation layout: NHWC fp32 ("pixel-major"): element (n,h,w,c) of a tensor with pixel stride PS
  * lives at base[((n*H + h)*W + w)*PS + c]; PS >= C lets several tensors share one concat buffer.
