@@ -19,6 +19,7 @@
  *   models/utils.py:186-204, layers/layers.py:15-29, layers/gdn.py:50-63          -> pcodec_conv_taps
  *   layers/win_attention.py:84-115,153-207    shifted-window attention core       -> pcodec_window_attention
  *   layers/masking.py:171-194 (cust_map)      custom importance-map masks          -> pcodec_slice_quantize_cust
+ *   models/CHProgREM.py:73-85,375-400         REM refinement gate                  -> pcodec_masked_residual
  *   (no reference equivalent) truncatable progressive container                   -> pcodec_layer_partition,
  *                                                                                    pcodec_rans_encode_segments / _decode_segments
  *
@@ -93,6 +94,15 @@ int pcodec_rans_decode_segments(const uint8_t *in_bytes, const int64_t *starts, 
                                 const int64_t *seg_start, const int32_t *seg_count, const int32_t *indexes,
                                 const int32_t *cdfs, int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
                                 int n_tables, int32_t *out_symbols, void *stream);
+
+/* REM wrapper (LatentRateReduction.forward tail + apply_latent_enhancement's attention mask, CHProgREM.py:73-85,
+ * 375-400): out = ret * (star - bar) + identity, where star / bar are the variance-aware masks of the ORIGINAL sigma
+ * at the current quality and at the preceding check level: mask_x = (mode_x == ONES) ? 1 : (mode_x == ZEROS) ? 0 :
+ * (sigma >= thr_x[b]).  ret / identity / out have `channels` channels (32, or 64 when mu_std: the 32-channel mask is
+ * used for both halves); sigma has 32 channels.  NHWC fp32 with pixel strides. */
+int pcodec_masked_residual(const float *ret, int ret_ps, const float *identity, int id_ps, const float *sigma,
+                           int sigma_ps, int batch, int64_t hw, int channels, int mode_star, const float *thr_star,
+                           int mode_bar, const float *thr_bar, float *out, int out_ps, void *stream);
 
 /* Progressive-layer partition of one 32-channel slice (replaces nothing in the reference: it turns the nested
  * variance-aware masks of masking.py:205-223 into an embedded layer order).  thresholds: float [n_levels][batch] in
@@ -201,6 +211,8 @@ int pcodec_bottleneck_likelihood(const float *z_hat, int z_ps, const float *para
 #define PCODEC_EPI_IGDN 6          /* r1 * sqrt(acc) */
 #define PCODEC_EPI_LRP 7           /* r1 + 0.5*tanh(acc) (+ r2 if given)     (CHProg_cnn.py:759-762, 840-843) */
 #define PCODEC_EPI_CLAMP01 8       /* min(max(acc,0),1)                      (CHProg_cnn.py:909, 988) */
+#define PCODEC_EPI_LEAKY 9         /* leaky_relu(acc, 0.01)                  (ResidualBlock, models/utils.py:59-87) */
+#define PCODEC_EPI_LEAKY_ADD 10    /* leaky_relu(acc, 0.01) + r1             (ResidualBlock output: + identity / skip) */
 
 #define PCODEC_FLAG_SQUARE_INPUT 1   /* A = x*x (GDN) */
 #define PCODEC_FLAG_PIXEL_SHUFFLE2 2 /* output channel co -> pixel (2h + (co>>1&1), 2w + (co&1)), channel co>>2; applied

@@ -11,6 +11,7 @@ from . import _lib, ans, checkpoint, container, evaluation, pipeline  # noqa: F4
 from ._lib import PcodecError, build_library  # noqa: F401
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional, pmf_to_quantized_cdf  # noqa: F401
 from .models import ChannelProgresssiveWACNN, get_scale_table  # noqa: F401
+from .rem import PostRateProcessedNetwork  # noqa: F401
 from .synthetic import apply_synthetic_weights  # noqa: F401
 
 models = {"channel": ChannelProgresssiveWACNN}

@@ -18,7 +18,7 @@ OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_OVERFLOW = 0, 1, 2, 3
 
 MASK_ONES, MASK_ZEROS, MASK_THRESHOLD = 0, 1, 2
 
-EPI_LINEAR, EPI_GELU, EPI_ADD, EPI_ADD_GELU, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP, EPI_CLAMP01 = range(9)
+EPI_LINEAR, EPI_GELU, EPI_ADD, EPI_ADD_GELU, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP, EPI_CLAMP01, EPI_LEAKY, EPI_LEAKY_ADD = range(11)
 FLAG_SQUARE_INPUT, FLAG_PIXEL_SHUFFLE2, FLAG_SUBPIXEL_NCHW = 1, 2, 4
 
 
@@ -63,6 +63,7 @@ PROTOTYPES = {
     "pcodec_rans_decode_ranges": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "pcodec_rans_encode_segments": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "pcodec_rans_decode_segments": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "pcodec_masked_residual": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "pcodec_layer_partition": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pcodec_selftest_rans_core_encode": (_i64, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _i64]),
     "pcodec_quantile_threshold": (_i, [_vp, _i, _i64, _i, _i, _f, _vp, _vp, _vp]),

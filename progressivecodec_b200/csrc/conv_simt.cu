@@ -64,6 +64,8 @@ __device__ __forceinline__ float apply_epilogue(int epi, float acc, float r1, fl
       return has_r2 ? __fadd_rn(v, r2) : v;
     }
     case PCODEC_EPI_CLAMP01: return fminf(fmaxf(acc, 0.f), 1.f);
+    case PCODEC_EPI_LEAKY: return acc > 0.f ? acc : __fmul_rn(0.01f, acc);
+    case PCODEC_EPI_LEAKY_ADD: return (acc > 0.f ? acc : __fmul_rn(0.01f, acc)) + r1;
     default: return acc;
   }
 }
@@ -274,7 +276,7 @@ static int validate(const pcodec_conv_desc *d) {
   if ((d->flags & PCODEC_FLAG_PIXEL_SHUFFLE2) && (d->cout % 4 != 0)) return PCODEC_ERR_BAD_ARG;
   const int epi = d->epilogue;
   const bool needs_r1 = epi == PCODEC_EPI_ADD || epi == PCODEC_EPI_ADD_GELU || epi == PCODEC_EPI_GATE ||
-                        epi == PCODEC_EPI_GDN || epi == PCODEC_EPI_IGDN || epi == PCODEC_EPI_LRP;
+                        epi == PCODEC_EPI_GDN || epi == PCODEC_EPI_IGDN || epi == PCODEC_EPI_LRP || epi == PCODEC_EPI_LEAKY_ADD;
   if (needs_r1 && !d->r1) return PCODEC_ERR_BAD_ARG;
   if (epi == PCODEC_EPI_GATE && !d->r2) return PCODEC_ERR_BAD_ARG;
   if ((d->flags & PCODEC_FLAG_PIXEL_SHUFFLE2) && needs_r1) return PCODEC_ERR_UNSUPPORTED;

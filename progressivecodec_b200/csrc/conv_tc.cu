@@ -233,6 +233,8 @@ __device__ __forceinline__ float tc_epilogue(int epi, float acc, float r1, float
       return has_r2 ? __fadd_rn(v, r2) : v;
     }
     case PCODEC_EPI_CLAMP01: return fminf(fmaxf(acc, 0.f), 1.f);
+    case PCODEC_EPI_LEAKY: return acc > 0.f ? acc : __fmul_rn(0.01f, acc);
+    case PCODEC_EPI_LEAKY_ADD: return (acc > 0.f ? acc : __fmul_rn(0.01f, acc)) + r1;
     default: return acc;
   }
 }
@@ -261,6 +263,8 @@ __device__ __noinline__ float4 tc_epilogue4(int epi, float4 v, float4 r1, float4
       else PC_EACH(__fadd_rn(p, __fmul_rn(0.5f, tanhf(a))));
       break;
     case PCODEC_EPI_CLAMP01: PC_EACH(fminf(fmaxf(a, 0.f), 1.f)); break;
+    case PCODEC_EPI_LEAKY: PC_EACH(a > 0.f ? a : __fmul_rn(0.01f, a)); break;
+    case PCODEC_EPI_LEAKY_ADD: PC_EACH((a > 0.f ? a : __fmul_rn(0.01f, a)) + p); break;
     default: o = v; break;
   }
 #undef PC_EACH

@@ -614,3 +614,36 @@ extern "C" int pcodec_layer_partition(const float *sigma, int sigma_ps, int batc
   }
   PCODEC_RETURN_LAUNCH();
 }
+
+// out = ret * (star - bar) + identity  (REM wrapper; see include/pcodec_b200.h)
+__global__ void __launch_bounds__(256)
+masked_residual_kernel(const float *__restrict__ ret, int ret_ps, const float *__restrict__ identity, int id_ps,
+                       const float *__restrict__ sigma, int sigma_ps, int64_t hw, int channels, int mode_star,
+                       const float *__restrict__ thr_star, int mode_bar, const float *__restrict__ thr_bar,
+                       float *__restrict__ out, int out_ps, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int c = (int)(e % channels);
+  const int64_t pix = e / channels;
+  const int b = (int)(pix / hw);
+  const float s = sigma[pix * sigma_ps + (c & 31)];
+  const float star = mode_star == PCODEC_MASK_ONES ? 1.f : (mode_star == PCODEC_MASK_ZEROS ? 0.f : (s >= thr_star[b] ? 1.f : 0.f));
+  const float bar = mode_bar == PCODEC_MASK_ONES ? 1.f : (mode_bar == PCODEC_MASK_ZEROS ? 0.f : (s >= thr_bar[b] ? 1.f : 0.f));
+  const float att = rintf(__fsub_rn(star, bar));  // apply_noise(mask, training=False) = torch.round
+  out[pix * out_ps + c] = __fadd_rn(__fmul_rn(ret[pix * ret_ps + c], att), identity[pix * id_ps + c]);
+}
+
+extern "C" int pcodec_masked_residual(const float *ret, int ret_ps, const float *identity, int id_ps, const float *sigma,
+                                      int sigma_ps, int batch, int64_t hw, int channels, int mode_star,
+                                      const float *thr_star, int mode_bar, const float *thr_bar, float *out, int out_ps,
+                                      void *stream) {
+  if (!ret || !identity || !sigma || !out || batch <= 0 || hw <= 0 || (channels != 32 && channels != 64))
+    return PCODEC_ERR_BAD_ARG;
+  if ((mode_star == PCODEC_MASK_THRESHOLD && !thr_star) || (mode_bar == PCODEC_MASK_THRESHOLD && !thr_bar))
+    return PCODEC_ERR_BAD_ARG;
+  const int64_t total = (int64_t)batch * hw * channels;
+  masked_residual_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
+      ret, ret_ps, identity, id_ps, sigma, sigma_ps, hw, channels, mode_star, thr_star, mode_bar, thr_bar, out, out_ps,
+      total);
+  PCODEC_RETURN_LAUNCH();
+}

@@ -488,6 +488,15 @@ class Engine:
                                                 p(out_b), p(counts), p(avail), 1 if avail is not None else 0,
                                                 self.stream()), "layer_partition")
 
+    def masked_residual(self, ret: Act, identity: Act, sigma: Act, mode_star: int, thr_star: Optional[Tensor],
+                        mode_bar: int, thr_bar: Optional[Tensor], out: Act) -> None:
+        """out = ret * round(star - bar) + identity (REM wrapper, CHProgREM.py:73-85, 375-400)."""
+        p = lambda t: t.data_ptr() if t is not None else None
+        assert ret.C == identity.C == out.C and sigma.C == 32
+        L.check(self.lib.pcodec_masked_residual(ret.ptr, ret.ps, identity.ptr, identity.ps, sigma.ptr, sigma.ps, ret.B,
+                                                ret.H * ret.W, ret.C, mode_star, p(thr_star), mode_bar, p(thr_bar),
+                                                out.ptr, out.ps, self.stream()), "masked_residual")
+
     def slice_dequantize(self, symbols: Tensor, mu: Act, y_hat: Act) -> None:
         L.check(self.lib.pcodec_slice_dequantize(symbols.data_ptr(), mu.ptr, mu.ps, mu.B, mu.H * mu.W, mu.C, y_hat.ptr,
                                                  y_hat.ps, self.stream()), "slice_dequantize")

@@ -175,3 +175,32 @@ class ChannelMask(_EngineOnly):
         if mask_pol == "two-levels":
             return ("zeros", None) if pr == 0 else ("ones", None)
         raise NotImplementedError(f"mask policy {mask_pol!r} is not on the B200 inference path")
+
+
+class ResidualBlock(_EngineOnly):
+    """models/utils.py:59-87: conv3x3 - LeakyReLU - conv3x3 - LeakyReLU, plus identity (1x1 `skip` conv when the channel
+    count changes).  Parameter container of the REM wrapper's LatentRateReduction nets."""
+
+    def __init__(self, in_ch: int, out_ch: int):
+        super().__init__()
+        self.conv1 = conv3x3(in_ch, out_ch)
+        self.nonlin = nn.LeakyReLU(inplace=True)
+        self.conv2 = conv3x3(out_ch, out_ch)
+        self.skip = conv1x1(in_ch, out_ch) if in_ch != out_ch else None
+
+
+class LatentRateReduction(_EngineOnly):
+    """CHProgREM.py:12-85 (module tree only; the arithmetic runs in rem.py on the CUDA engine)."""
+
+    def __init__(self, dim_chunk: int = 32, mu_std: bool = False, dimension: str = "middle"):
+        super().__init__()
+        self.dim_block = dim_chunk
+        self.mu_std = mu_std
+        N = dim_chunk
+        extra = 1 if dimension == "big" else 0
+        self.enc_base_entropy_params = nn.Sequential(ResidualBlock(2 * N, N), *[ResidualBlock(N, N) for _ in range(1 + extra)])
+        self.enc_enh_entropy_params = nn.Sequential(ResidualBlock(2 * N if mu_std else N, N),
+                                                    *[ResidualBlock(N, N) for _ in range(1 + extra)])
+        self.enc_base_rep = nn.Sequential(*[ResidualBlock(N, N) for _ in range(2 + extra)])
+        self.enc = nn.Sequential(ResidualBlock(3 * N, 2 * N), *[ResidualBlock(2 * N, 2 * N) for _ in range(1 + extra)],
+                                 ResidualBlock(2 * N, 2 * N if mu_std else N))

@@ -412,7 +412,7 @@ class ChannelProgresssiveWACNN(nn.Module):
         return out
 
     # -- the two slice loops -----------------------------------------------------------------------------------
-    def _base_slices(self, P, lm: Act, ls: Act, code, code_many=None):
+    def _base_slices(self, P, lm: Act, ls: Act, code, code_many=None, record: Optional[list] = None):
         """Base loop (CHProg_cnn.py:507-544 / 729-764 / 874-904).  `code(i, mu, scale, y_pre)` performs the
         quantise-or-decode step and must fill y_pre (= symbols + mu).
 
@@ -436,6 +436,8 @@ class ChannelProgresssiveWACNN(nn.Module):
             mu, scale = E.act(B, h, w, 32), E.act(B, h, w, 32)
             self._stack(E, P["cc_mean_transforms"][i], [lm0] + sup, mu)
             self._stack(E, P["cc_scale_transforms"][i], [ls0] + sup, scale)
+            if record is not None:  # REM wrapper: the base slices' (mu, sigma) feed the refinement nets
+                record.append((mu, scale))
             return mu, scale
 
         def refine(i, y_pre):
@@ -461,7 +463,7 @@ class ChannelProgresssiveWACNN(nn.Module):
 
     def _prog_slices(self, P, lm: Act, ls: Act, y_hat_base: Act, quality, mask_pol, code, mode: str,
                      state: Optional[dict] = None, residual_before_lrp: bool = False, deferred: Optional[list] = None,
-                     cust_map: Optional[Act] = None):
+                     cust_map: Optional[Act] = None, refine=None):
         """Progressive loop (CHProg_cnn.py:576-642 / 775-845 / 921-983 / 1091-1166).
         `code(i, mu, scale, mask_mode, thr, y_pre)`; `mode` in {"forward","fsq","codec"} selects the
         mu_total / std_total bookkeeping of that entry point (only observable with all_scalable)."""
@@ -514,6 +516,8 @@ class ChannelProgresssiveWACNN(nn.Module):
                 else:
                     std_total.append(scale if self.support_std else mut)
                     mu_total.append(mut)
+            if refine is not None:  # REM wrapper: apply_latent_enhancement (CHProgREM.py:375-431), after the bookkeeping
+                mu, scale = refine(i, mu, scale, base_i)
             cm_i = cust_map.slice(32 * i, 32) if cust_map is not None else None  # cust_map.chunk(10, 1)[i], CHProg_cnn.py:721
             thr = E.quantile_threshold(cm_i if cm_i is not None else scale, q) if mask_mode == L.MASK_THRESHOLD else None
             y_pre = E.act(B, h, w, 32)
@@ -671,7 +675,7 @@ class ChannelProgresssiveWACNN(nn.Module):
 
     @torch.no_grad()
     def compress(self, x, quality=0.0, mask_pol=None, cust_map=None, return_device_streams: bool = False,
-                 debug: Optional[dict] = None):
+                 debug: Optional[dict] = None, _rem=None):
         """CHProg_cnn.py:686-847.  One batched rANS launch codes every (slice, image) stream.
         `debug` (tests only) receives the device symbol / index planes [n_slices, B, 32*h*w] and z symbols."""
         mask_pol = self.mask_policy if mask_pol is None else mask_pol
@@ -690,8 +694,10 @@ class ChannelProgresssiveWACNN(nn.Module):
             E.slice_quantize(y.slice(32 * i, 32), None, mu, scale, L.MASK_ONES, None, table, bound, sym[i], idx[i], None,
                              None, y_pre)
 
-        y_hat_base = self._base_slices(P, lm, ls, code_base)
+        record: Optional[list] = [] if _rem is not None else None
+        y_hat_base = self._base_slices(P, lm, ls, code_base, record=record)
         masks: List[Tensor] = []
+        y_hat_out = y_hat_base
         if quality > 0:
             def code_prog(i, mu, scale, mask_mode, thr, y_pre, mask_src=None):
                 m = torch.empty((B, 32, h, w), dtype=torch.float32, device=E.device)
@@ -700,21 +706,25 @@ class ChannelProgresssiveWACNN(nn.Module):
                                  sym[self.ns0 + i], idx[self.ns0 + i], m, None, y_pre, mask_src=mask_src)
                 masks.append(m)
 
-            self._prog_slices(P, lm, ls, y_hat_base, quality, mask_pol, code_prog, "codec",
-                              cust_map=self._cust_map_act(E, cust_map, B, h, w))
+            refine = None
+            if _rem is not None:
+                refine = lambda i, mu, scale, base_i: _rem._refine(E, quality, mask_pol, i, mu, scale, base_i, record)
+            y_hat_out = self._prog_slices(P, lm, ls, y_hat_base, quality, mask_pol, code_prog, "codec",
+                                          cust_map=self._cust_map_act(E, cust_map, B, h, w), refine=refine)
         if debug is not None:
             debug.update(symbols=sym, indexes=idx, z_symbols=z_sym, y=E.to_nchw(y), y_hat_base=E.to_nchw(y_hat_base))
         z_data, z_off = _ans.encode_batch(z_sym, z_idx, P["eb_tables"])
         y_data, y_off = _ans.encode_batch(sym.reshape(n_slices * B, n), idx.reshape(n_slices * B, n), P["gc_tables"])
         shape = torch.Size([z.H, z.W])
+        extra = {"y_hat": E.to_nchw(y_hat_out)} if _rem is not None else {}
         if return_device_streams:
-            return {"streams": (y_data, y_off, z_data, z_off), "shape": shape, "masks": masks, "batch": B}
+            return {"streams": (y_data, y_off, z_data, z_off), "shape": shape, "masks": masks, "batch": B, **extra}
         flat = _ans.split_streams(y_data, y_off)
         y_strings = [flat[s * B:(s + 1) * B] for s in range(n_slices)]
-        return {"strings": [y_strings, _ans.split_streams(z_data, z_off)], "shape": shape, "masks": masks}
+        return {"strings": [y_strings, _ans.split_streams(z_data, z_off)], "shape": shape, "masks": masks, **extra}
 
     @torch.no_grad()
-    def decompress(self, strings, shape, quality, mask_pol=None, cust_map=None, _worker: int = 0):
+    def decompress(self, strings, shape, quality, mask_pol=None, cust_map=None, _worker: int = 0, _rem=None):
         """CHProg_cnn.py:849-999.
 
         `_worker` (not part of the reference API) gives concurrent decompress() calls from different host threads their
@@ -741,8 +751,9 @@ class ChannelProgresssiveWACNN(nn.Module):
         groups = max(1, min(groups, B))
         if groups == 1:
             # slot 1, not 0: slot 0 belongs to the encoder-side entry points, which pipeline.sweep() runs concurrently
-            return {"x_hat": self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, 0, B, shape, quality,
-                                                    mask_pol, slot=1 + 8 * _worker, cust_map=cust_map)}
+            out = self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, 0, B, shape, quality, mask_pol,
+                                         slot=1 + 8 * _worker, cust_map=cust_map, rem=_rem)
+            return {"x_hat": out[0], "y_hat": out[1]} if _rem is not None else {"x_hat": out}
         import threading
 
         from .sharding import shard_bounds
@@ -766,7 +777,8 @@ class ChannelProgresssiveWACNN(nn.Module):
                 with torch.cuda.device(dev), torch.cuda.stream(st), torch.no_grad():
                     outs[g] = self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, lo, hi, shape,
                                                      quality, mask_pol, slot=g + 1 + 8 * _worker,
-                                                     cust_map=cust_map[lo:hi] if cust_map is not None else None)
+                                                     cust_map=cust_map[lo:hi] if cust_map is not None else None,
+                                                     rem=_rem)
             except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
                 errs[g] = e
 
@@ -780,10 +792,14 @@ class ChannelProgresssiveWACNN(nn.Module):
                 raise e
         for g in range(groups):
             cur.wait_stream(streams[g])
-            outs[g].record_stream(cur)
+            for t in (outs[g] if _rem is not None else (outs[g],)):
+                t.record_stream(cur)
+        if _rem is not None:
+            return {"x_hat": torch.cat([o[0] for o in outs], 0), "y_hat": torch.cat([o[1] for o in outs], 0)}
         return {"x_hat": torch.cat(outs, 0)}
 
-    def _decode_base(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, enhanced: bool, slot: int):
+    def _decode_base(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, enhanced: bool, slot: int,
+                     record: Optional[list] = None):
         """z + the 10 base slices of images [lo, hi) of a batch whose streams are laid out slice-major
         (stream (s, b) = s*B_total + b).  Returns (lm, ls, y_hat_base, decode_slice)."""
         E: Engine = P["eng"]
@@ -823,7 +839,7 @@ class ChannelProgresssiveWACNN(nn.Module):
 
         y_hat_base = self._base_slices(
             P, lm, ls, lambda i, mu, scale, y_pre: decode_slice(i, scale, L.MASK_ONES, None, mu, y_pre),
-            code_many=decode_many if self.batch_independent_slices else None)
+            code_many=decode_many if self.batch_independent_slices else None, record=record)
         return lm, ls, y_hat_base, decode_slice
 
     def _cust_map_act(self, E: Engine, cust_map, B: int, h: int, w: int) -> Optional[Act]:
@@ -838,16 +854,22 @@ class ChannelProgresssiveWACNN(nn.Module):
         return E.from_nchw(cust_map)
 
     def _decompress_group(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, quality, mask_pol,
-                          slot: int = 0, cust_map=None):
+                          slot: int = 0, cust_map=None, rem=None):
         """Decode images [lo, hi) of a batch whose streams are laid out slice-major: stream (s, b) = s*B_total + b."""
+        record: Optional[list] = [] if rem is not None else None
         lm, ls, y_hat_base, decode_slice = self._decode_base(P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi,
-                                                             shape, enhanced=not (quality == 0), slot=slot)
-        if quality == 0:
-            return self._g_s(P, y_hat_base, 0, clamp=True)
+                                                             shape, enhanced=not (quality == 0), slot=slot, record=record)
         E = P["eng"]
+        if quality == 0:
+            x_hat = self._g_s(P, y_hat_base, 0, clamp=True)
+            return (x_hat, E.to_nchw(y_hat_base)) if rem is not None else x_hat
+        refine = None
+        if rem is not None:
+            refine = lambda i, mu, scale, base_i: rem._refine(E, quality, mask_pol, i, mu, scale, base_i, record)
         y_hat_q = self._prog_slices(
             P, lm, ls, y_hat_base, quality, mask_pol,
             lambda i, mu, scale, mask_mode, thr, y_pre, mask_src=None: decode_slice(self.ns0 + i, scale, mask_mode, thr, mu,
                                                                                     y_pre, mask_src),
-            "codec", cust_map=self._cust_map_act(E, cust_map, lm.B, lm.H, lm.W))
-        return self._g_s(P, y_hat_q, 1, clamp=True)
+            "codec", cust_map=self._cust_map_act(E, cust_map, lm.B, lm.H, lm.W), refine=refine)
+        x_hat = self._g_s(P, y_hat_q, 1, clamp=True)
+        return (x_hat, E.to_nchw(y_hat_q)) if rem is not None else x_hat
