@@ -43,7 +43,7 @@ struct TcWeights {
   CUtensorMap map_hi, map_lo;
   float *dev_hi, *dev_lo;  // [cout][k_total]
   int cout, k_total, bn, n_tiles;
-  int small;  // 1: two-CTAs-per-SM variant (short reductions): bn <= 64, <= 256 TMEM columns, <= 3 stages
+  int small;  // two-CTAs-per-SM variant: 1 = separate lo accumulator (bn <= 64), 2 = lo products share the hi accumulator (bn <= 128)
 };
 
 struct TcParams {
@@ -53,6 +53,7 @@ struct TcParams {
   int raw_stages;  // debug knob bits (PCODEC_TC_DEBUG): 1 = skip A global loads, 2 = skip B TMA loads, 4 = skip converter TMEM stores
   int n_hi_acc;  // TMEM accumulators for the hi*hi products (round-robin over K slabs); +1 for the lo terms when split
   int a_ring;    // depth of the A operand ring in tensor memory (2..4)
+  int shared_lo;  // 1: the lo products accumulate into hi accumulator 0 (short reductions: <= ~300 MMAs in total)
   uint32_t magic_w, magic_h;  // division by grid_w / grid_h as one multiply (dividends < 2^31): q = (m * magic) >> (31 + shift)
   int shift_w, shift_h;
 };
@@ -333,7 +334,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   // A ring: refilling an A buffer after its MMAs retire takes ~800 clk (commit -> converter wake-up -> tcgen05.st ->
   // wait::st -> arrive -> issuer wake-up) against 480..670 clk of MMA work per slab, so two buffers leave the tensor
   // pipe idle half the time (measured with the clock64 timeline, tools/trace_tc.py); three hide the round trip.
-  const int n_acc = P.n_hi_acc + (split ? 1 : 0);
+  const int n_acc = P.n_hi_acc + ((split && !P.shared_lo) ? 1 : 0);
   const int a_cols = split ? 64 : 32;            // hi (32 fp32 columns) + lo (32)
   const int a_ring = P.a_ring;
   const uint32_t a_tmem_off = (uint32_t)(n_acc * bn);
@@ -534,7 +535,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     uint32_t acc_mask = 0;
     for (int j = 0; j < P.n_hi_acc; ++j)
       if (n_steps > j) acc_mask |= 1u << j;
-    if (split) acc_mask |= 1u << P.n_hi_acc;
+    if (split && !P.shared_lo) acc_mask |= 1u << P.n_hi_acc;
     if (d.flags & PCODEC_FLAG_SUBPIXEL_NCHW) {
       // Image layer: conv channel (2*py + px) * C + c  ->  out[n][c][2h + py][2w + px] (NCHW, out_h x out_w = 2 x grid).
       // A thread owns pixel (h, w); consecutive lanes are consecutive w, so each (c, py) is one 8-byte store per lane
@@ -704,7 +705,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     {
       // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t acc_lo = tmem_acc + (uint32_t)(P.n_hi_acc * bn);
+      const uint32_t acc_lo = P.shared_lo ? tmem_acc : tmem_acc + (uint32_t)(P.n_hi_acc * bn);
       int st = 0, hi_idx = 0, q = 0;
       uint32_t qph = 0;
       // tcgen05.commit returns only when the queued MMAs have (nearly) retired, so every cycle between a commit and
@@ -728,7 +729,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
             const uint32_t ak = (uint32_t)(k * 8);   // A: 8 fp32 columns of tensor memory
             umma_tf32_ts(acc_hi, ta_hi + ak, db_hi + adv, idesc, (!first_hi || k > 0) ? 1u : 0u);
             if (split) {
-              umma_tf32_ts(acc_lo, ta_lo + ak, db_hi + adv, idesc, (s > 0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(acc_lo, ta_lo + ak, db_hi + adv, idesc, (P.shared_lo || s > 0 || k > 0) ? 1u : 0u);
               umma_tf32_ts(acc_lo, ta_hi + ak, db_lo + adv, idesc, 1u);
             }
           }
@@ -816,17 +817,21 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
                                       void *stream) {
   if (!w_tap_major || !handle_out || n_taps < 1 || cin_total < 4 || cout < 1) return PCODEC_ERR_BAD_ARG;
   *handle_out = nullptr;
-  // short reductions (<= 20 K slabs: the 1x1 convolutions, GDN, Linear layers) use the two-CTAs-per-SM variant
   const int n_slabs = (n_taps * cin_total + TC_BK - 1) / TC_BK;
-  // Opt-in only (PCODEC_TC_SMALL=1: cout <= 64; =2: also every 1-tap reduction of <= 20 slabs): on this model it measured
-  // equal or slower than one CTA per SM — for 192-wide 1x1 layers it needs more N tiles (more A re-reads), and for the
-  // narrow slice-stack layers two resident CTAs did not raise the per-SM throughput.
-  bool small = false;
-  if (const char *e = getenv("PCODEC_TC_SMALL")) {
-    const int v = atoi(e);
-    small = (v >= 1 && cout <= 64) || (v >= 2 && n_taps == 1 && n_slabs <= 20);
-  }
-  const int bn = small ? pick_bn(cout, n_taps * cin_total, 64, 256) : pick_bn(cout, n_taps * cin_total);
+  // Default: only 1-tap reductions of <= 24 slabs whose whole output fits ONE tile of <= 128 columns (the ResidualUnit
+  // 1x1 192->96: -23 %).  With so few MMAs (<= 288) the lo products can share the hi accumulator, so the tile needs
+  // bn + 128 <= 256 TMEM columns and ~82 KB of shared memory, and two CTAs overlap each other's prologue / epilogue.
+  // For wider outputs the variant needs more N tiles (more A re-reads) and measured equal or slower; for the narrow 3x3
+  // slice-stack layers two resident CTAs did not raise the per-SM throughput.  PCODEC_TC_SMALL: 0 = never, 1 = also
+  // every cout <= 64 layer, 2 = also every 1-tap short reduction (separate lo accumulator, bn <= 64), 3 = as 2 with the
+  // shared accumulator (bn <= 128).
+  int mode = -1;
+  if (const char *e = getenv("PCODEC_TC_SMALL")) mode = atoi(e);
+  const bool short_1tap = n_taps == 1 && n_slabs <= 24;
+  bool small = mode < 0 ? (short_1tap && cout <= 128) : ((mode >= 1 && cout <= 64) || (mode >= 2 && short_1tap));
+  const bool shared = small && short_1tap && (mode < 0 || mode >= 3);
+  const int bn = small ? pick_bn(cout, n_taps * cin_total, shared ? 128 : 64, shared ? 256 + 128 : 256)
+                       : pick_bn(cout, n_taps * cin_total);
   if (bn == 0 || (cin_total % 4) != 0) return PCODEC_ERR_UNSUPPORTED;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return PCODEC_ERR_UNSUPPORTED;
@@ -835,7 +840,7 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
   h->k_total = n_taps * cin_total;
   h->bn = bn;
   h->n_tiles = (cout + bn - 1) / bn;
-  h->small = small ? 1 : 0;
+  h->small = small ? (shared ? 2 : 1) : 0;
   const size_t bytes = sizeof(float) * (size_t)cout * h->k_total;
   if (cudaMalloc(&h->dev_hi, bytes) != cudaSuccess || cudaMalloc(&h->dev_lo, bytes) != cudaSuccess) {
     delete h;
@@ -941,6 +946,11 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
     if (const char *e = getenv("PCODEC_TC_RING")) {  // experiment knob
       ring = std::max(2, std::min(4, atoi(e)));
       n_acc = (tmem_limit - ring * a_cols) / h->bn;
+    }
+    P.shared_lo = 0;
+    if (h->small == 2) {  // single shared accumulator
+      P.shared_lo = 1;
+      n_acc = 1 + (split3 ? 1 : 0);
     }
     int n_hi = n_acc - (split3 ? 1 : 0);
     if (n_hi > 4) n_hi = 4;
