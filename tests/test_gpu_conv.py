@@ -9,6 +9,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 RTOL = 2e-5  # fp32 accumulation-order noise, relative to the output's RMS
+L_EPI_GELU = 1  # progressivecodec_b200._lib.EPI_GELU
 
 
 def _engine(impl=0):
@@ -299,3 +300,22 @@ def test_tc_merged_image_layer(hw, batch):
     assert got.shape == ref.shape
     _close(got.cpu(), ref)
     _close(E.deconv_image(pc, _nhwc(x), L.EPI_CLAMP01).cpu(), ref.clamp(0, 1))
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
+def test_tc_two_cta_variants_match_torch(mode, monkeypatch):
+    """The 10-warp two-CTAs-per-SM kernel variant (PCODEC_TC_SMALL picks where it is used; default = 1-tap short
+    reductions with cout <= 128) against torch, for the tile shapes each mode produces."""
+    from progressivecodec_b200.engine import pack_conv2d
+
+    monkeypatch.setenv("PCODEC_TC_SMALL", mode)
+    E = _engine()
+    torch.manual_seed(int(mode))
+    for cin, cout, k, hw in ((192, 96, 1, (24, 40)), (96, 192, 1, (24, 40)), (128, 64, 3, (16, 24)), (64, 32, 3, (16, 24)),
+                             (640, 320, 1, (8, 12))):
+        m = nn.Conv2d(cin, cout, k, 1, k // 2)
+        x = torch.randn(3, cin, *hw)
+        pc = pack_conv2d(m, E.device, f"c{cin}_{cout}").attach_tc(3)
+        assert pc.tc is not None
+        got = E.conv_new(pc, [_nhwc(x)], L_EPI_GELU)
+        _close(_nchw(got), F.gelu(m(x)).detach())
