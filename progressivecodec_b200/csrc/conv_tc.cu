@@ -1,27 +1,33 @@
 // tcgen05 / TMEM / TMA implicit-GEMM convolution ("sum of shifted-tap GEMMs") with 3xTF32 split accumulation.
 //
 // Same contract as the SIMT kernel (conv_simt.cu) but the contraction runs on the 5th-gen tensor cores:
-//   * CTA tile 128 (output pixels) x BN (output channels, 16..256), K slab = 32 input channels of one tap.
+//   * CTA tile 128 (output pixels) x BN (output channels, 16..256, chosen per layer so that enough accumulators fit
+//     tensor memory; the last N tile may be padded), K slab = 32 input channels of one tap.
 //   * B (weights, K-major [Cout][T*Cin] fp32, pre-split on the host into TF32 hi and lo parts) arrives by TMA
-//     (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage ring; OOB columns of the last slab are
-//     zero-filled by the TMA unit.
+//     (cp.async.bulk.tensor.2d, 128-byte swizzle) into a multi-stage ring; out-of-range rows / columns are zero-filled
+//     by the TMA unit.
 //   * A (activations) is an on-the-fly gather of the shifted NHWC patch (padding / stride / virtual concat in the
 //     address math).  Four loader warps copy it with 16-byte cp.async (LDGSTS, zero-fill for padding) into a
-//     shared-memory staging tile; four converter warps read one tile ROW per thread, form lo = x - trunc_tf32(x)
-//     (and x*x for GDN) and write hi (= the raw fp32: kind::tf32 ignores the low 13 mantissa bits, verified) and
-//     lo with tcgen05.st into a double-buffered A operand area of TENSOR MEMORY.
-//   * One elected thread issues tcgen05.mma.kind::tf32 in the TS form (A from TMEM, B from shared memory):
-//     acc += Ahi*Bhi ; acc_lo += Alo*Bhi + Ahi*Blo.  A in TMEM matters: in the SS form the operand fetch from
-//     shared memory (~64 B/clk) re-read the 4 KB A tile for every one of the 3 products and capped the kernel at
-//     ~43 % of the MMA rate for N = 96 (measured: time per MMA == (A bytes + B bytes)/64).
+//     shared-memory staging tile; NG groups of four converter warps take alternate K slabs, read one tile ROW per
+//     thread, form lo = x - trunc_tf32(x) (and x*x for GDN) and write hi (= the raw fp32: kind::tf32 ignores the low
+//     13 mantissa bits, verified) and lo with tcgen05.st into a 2..3-deep A operand ring in TENSOR MEMORY.
+//   * One thread chosen with elect.sync runs the whole MMA issue loop: tcgen05.mma.kind::tf32 in the TS form (A from
+//     TMEM, B from shared memory), acc_hi[s % n_hi] += Ahi*Bhi ; acc_lo += Alo*Bhi + Ahi*Blo, 12 instructions per slab
+//     issued straight-line, then ONE tcgen05.commit that releases both the weight stage and the A buffer.
+//     A in TMEM matters: in the SS form the operand fetch from shared memory re-read the 4 KB A tile for each of the 3
+//     products.  Several accumulators matter: the tensor core truncates (RZ) once per MMA per accumulator, so long
+//     reductions are spread over up to 4 hi accumulators + 1 lo accumulator and summed with RN adds in the epilogue.
 //     The dropped Alo*Blo term is ~2^-22 relative, i.e. fp32-class accuracy, which the codec needs because these
 //     outputs feed round(), sigma->CDF-index thresholds and the quantile ranking.
-//     `tc_split = 1` issues only the first product (plain TF32) — for layers whose output only enters PSNR.
-//   * tcgen05.commit releases ring slots / A buffers and finally signals the epilogue; all eight producer warps
-//     then read the accumulators with tcgen05.ld (one TMEM lane = one output pixel per thread), sum the partial
-//     accumulators, apply the fused epilogue (bias / GELU / residual / gate / GDN / LRP / clamp / pixel-shuffle)
-//     and store 64-byte runs per thread.
+//     `tc_split = 1` issues only the first product (plain TF32).
+//   * Epilogue by all producer warps: tcgen05.ld (one TMEM lane = one output pixel per thread), sum of the partial
+//     accumulators, a 32x16 transpose through shared memory so that residual loads / output stores are 64-byte runs,
+//     fused bias / GELU / LeakyReLU / residual / gate / GDN / LRP / clamp (one vectorised switch), or the
+//     pixel-shuffle / sub-pixel-NCHW stores.  Residual tiles are prefetched into L2 at kernel start.
+//   * Two instantiations: <2> 14 warps, one CTA per SM (long reductions); <1> 10 warps, <= 256 TMEM columns, two CTAs
+//     per SM (1-tap short reductions whose output fits one tile; see pcodec_conv_tc_prepare).
 // The K order (segment, tap, channel slab; hi*hi, lo*hi, hi*lo) is fixed: deterministic and batch invariant.
+// What shaped this design is recorded in DESIGN.md §3.1 (measurements: tools/trace_tc.py, tools/ubench/mma_rate.cu).
 #include <cuda.h>
 
 #include <algorithm>
@@ -50,7 +56,8 @@ struct TcParams {
   pcodec_conv_desc d;
   int64_t M;
   int bn, stages, split, n_steps;
-  int raw_stages;  // debug knob bits (PCODEC_TC_DEBUG): 1 = skip A global loads, 2 = skip B TMA loads, 4 = skip converter TMEM stores
+  int debug;  // PCODEC_TC_DEBUG bits: 1 = skip A global loads, 2 = skip B TMA loads, 4 = skip converter TMEM stores (timing
+              // experiments, wrong results), 64 = record the clock64 timeline of one CTA (128: a mid-grid CTA)
   int n_hi_acc;  // TMEM accumulators for the hi*hi products (round-robin over K slabs); +1 for the lo terms when split
   int a_ring;    // depth of the A operand ring in tensor memory (2..4)
   int shared_lo;  // 1: the lo products accumulate into hi accumulator 0 (short reductions: <= ~300 MMAs in total)
@@ -111,16 +118,6 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// wait until at most `n` of this thread's most recent cp.async groups are still in flight (n is warp-uniform, 0..3)
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-  switch (n) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-  }
-}
 // One lane polls the barrier, the warp converges behind it: an mbarrier op per THREAD (128 try_waits + 128 arrives
 // per barrier per K slab) serialises in the shared-memory unit and was the whole per-slab cost of the v5 pipeline
 // (measured: ~1200 clk per slab with every load, TMEM store and 2 of 3 MMAs removed).
@@ -155,18 +152,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, M=128, N from idesc, K=8
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// same with the A operand in tensor memory (TS form): A = 128 lanes x 8 columns of fp32 at tmem_a
+// D[tmem] (+)= A[tmem] * B[smem], kind::tf32, M=128, N from idesc, K=8 (TS form): A = 128 lanes x 8 columns of fp32 at tmem_a
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -299,8 +285,8 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   const pcodec_conv_desc &d = P.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = P.bn, stages = P.stages;
-  const bool trace = (P.raw_stages & 64) && blockIdx.x == ((P.raw_stages & 128) ? gridDim.x / 2 : 0) &&
-                     blockIdx.y == ((P.raw_stages & 128) ? gridDim.y - 1 : 0) && lane == 0;
+  const bool trace = (P.debug & 64) && blockIdx.x == ((P.debug & 128) ? gridDim.x / 2 : 0) &&
+                     blockIdx.y == ((P.debug & 128) ? gridDim.y - 1 : 0) && lane == 0;
   if (threadIdx.x == 0) TC_TRACE_G(0);
   const bool split = P.split == 3;
   const int b_bytes = bn * 128;
@@ -313,15 +299,14 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
   auto b_lo = [&](int s) { return b_hi(s) + b_bytes; };
   // the stage area doubles as the epilogue's transpose scratch (2 KB per producer warp)
   const uint32_t bar_base = smem_base + max(stages * stage_bytes, TC_PRODUCER_WARPS * 2048);
-  auto raw_full = [&](int s) { return bar_base + 8u * s; };                   // cp.async landed        (128 loaders)
-  auto raw_empty = [&](int s) { return bar_base + 8u * (stages + s); };       // staging tile consumed  (128 converters)
+  auto raw_full = [&](int s) { return bar_base + 8u * s; };                   // cp.async landed        (128 loader threads)
+  auto raw_empty = [&](int s) { return bar_base + 8u * (stages + s); };       // staging tile consumed  (4 converter warps)
   auto full_b = [&](int s) { return bar_base + 8u * (2 * stages + s); };      // TMA bytes landed
   // `empty_b(st)` = "slab in ring slot st consumed": ONE tcgen05.commit per slab releases both the B stage (to the
   // TMA producer, a ring of `stages`) and the A operand buffer (to the converter group, which waits for the slot of
-  // slab s-2).  A commit costs the issuing thread ~150 clk, so one per slab instead of two matters.
+  // slab s - a_ring).  A commit costs the issuing thread ~150 clk, so one per slab instead of two matters.
   auto empty_b = [&](int s) { return bar_base + 8u * (3 * stages + s); };     // MMAs of the slab in this slot done (tcgen05.commit)
-  auto a_full = [&](int q) { return bar_base + 8u * (4 * stages + q); };      // A operand in TMEM      (128 converters)
-  auto a_empty = [&](int q) { return bar_base + 8u * (4 * stages + 2 + q); }; // MMAs that read it done (tcgen05.commit)
+  auto a_full = [&](int q) { return bar_base + 8u * (4 * stages + q); };      // A ring slot q (0..3) filled (4 converter warps)
   const uint32_t tmem_full = bar_base + 8u * (4 * stages + 4);
   const uint32_t tmem_slot = tmem_full + 8u;
   uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
@@ -443,7 +428,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
           if (warp == 0) TC_TRACE(s, 0);
           const uint32_t dst = a_raw(st);
           const uint32_t mask = (kc * TC_BK + chunk * 4 < seg_channels) ? rowmask : 0u;
-          if (!(P.raw_stages & 1)) {
+          if (!(P.debug & 1)) {
 #pragma unroll
             for (int i = 0; i < RPT; ++i)
               cp_async16(dst + soff[i], rowptr[i] + kc * TC_BK, ((mask >> i) & 1u) ? 16u : 0u);
@@ -490,9 +475,9 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         if ((warp & 3) == 0) TC_TRACE(s, 4);
         tc_fence_after();
         const uint32_t ta = lane_base + (uint32_t)(q * a_cols);
-        if (!(P.raw_stages & 4)) tmem_st32(ta, x);
+        if (!(P.debug & 4)) tmem_st32(ta, x);
         mbar_arrive_warp(raw_empty(st), lane);  // staging tile consumed (the TMEM store has read the registers)
-        if (split && !(P.raw_stages & 4)) {
+        if (split && !(P.debug & 4)) {
           float4 l[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -682,7 +667,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         if (st == stages) { st = 0; ph ^= 1u; }
         mbar_wait(empty_b(st), ph);
         const int k = tap * d.cin_total + seg_cbase + kc * TC_BK;
-        if (P.raw_stages & 2) {
+        if (P.debug & 2) {
           mbar_arrive(full_b(st));
         } else {
           mbar_expect_tx(full_b(st), (uint32_t)((split ? 2 : 1) * b_bytes));
@@ -930,8 +915,8 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   if (stages > n_steps) stages = n_steps;
   if (stages < 1 || need(stages) > smem_limit) return PCODEC_ERR_UNSUPPORTED;
   P.stages = stages;
-  P.raw_stages = 0;
-  if (const char *e = getenv("PCODEC_TC_DEBUG")) P.raw_stages = atoi(e);  // experiment knob (wrong results!)
+  P.debug = 0;
+  if (const char *e = getenv("PCODEC_TC_DEBUG")) P.debug = atoi(e);  // experiment knob (wrong results!)
   {
     // TMEM columns: (n_hi hi accumulators + 1 lo) of bn columns + a_ring A operand buffers (hi 32 [+ lo 32] columns).
     // Prefer a 3-deep A ring; spend what is left on hi accumulators (up to 4).
