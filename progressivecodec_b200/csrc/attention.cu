@@ -93,6 +93,10 @@ window_attention_v4_kernel(const float *__restrict__ qkv, int qkv_ps, float *__r
                            const float *__restrict__ rel_bias, int H, int W, int C, int heads, int ws, int shift) {
   __shared__ __align__(16) float sk[T * HD];
   __shared__ __align__(16) float sv[T * HD];
+  // the head's relative-position bias, staged through shared memory: thread i needs ROW i (bias[i][0..T)), and reading
+  // it straight from global memory costs 32 L1 wavefronts per load instruction (rows are T floats apart) — measured:
+  // those loads, not the FMAs, bounded the kernel.  Coalesced load + padded rows (T + 1) make both sides conflict free.
+  __shared__ float s_bias[T * (T + 1)];
   __shared__ int s_region[T];
   const int nww = W / ws, nwh = H / ws;
   const int win = blockIdx.x % (nwh * nww);
@@ -124,10 +128,13 @@ window_attention_v4_kernel(const float *__restrict__ qkv, int qkv_ps, float *__r
       region = rh * 3 + rw;
     }
     s_region[i] = region;
+    const float *hb = rel_bias + (int64_t)head * T * T;
+#pragma unroll 8
+    for (int e = i; e < T * T; e += T) s_bias[(e / T) * (T + 1) + (e % T)] = __ldg(hb + e);
   }
   __syncthreads();
   float s[T];
-  const float *bias = rel_bias + ((int64_t)head * T + i) * T;
+  const float *bias = s_bias + i * (T + 1);
   const int my_region = s_region[i];
   float mx = -INFINITY;
 #pragma unroll
@@ -141,7 +148,7 @@ window_attention_v4_kernel(const float *__restrict__ qkv, int qkv_ps, float *__r
       acc = fmaf(q[4 * c + 2], k4.z, acc);
       acc = fmaf(q[4 * c + 3], k4.w, acc);
     }
-    float v = acc + __ldg(bias + j);
+    float v = acc + bias[j];
     if (shift > 0 && s_region[j] != my_region) v += -100.0f;
     s[j] = v;
     mx = fmaxf(mx, v);
