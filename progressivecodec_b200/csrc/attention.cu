@@ -189,23 +189,30 @@ int launch_attention_v4(const float *qkv, int qkv_ps, float *out, int out_ps, co
   PCODEC_RETURN_LAUNCH();
 }
 
-__global__ void im2col_nchw_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int H, int W, int k,
-                                   int stride, int pad, int OH, int OW, int k_pad, int64_t total) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int kk = (int)(e % k_pad);
-  int64_t t = e / k_pad;
-  const int ow = (int)(t % OW); t /= OW;
-  const int oh = (int)(t % OH);
-  const int64_t n = t / OH;
-  float v = 0.f;
-  if (kk < k * k * C) {
-    const int c = kk % C, tap = kk / C;
-    const int ky = tap / k, kx = tap % k;
-    const int iy = oh * stride + ky - pad, ix = ow * stride + kx - pad;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(src + ((n * C + c) * H + iy) * (int64_t)W + ix);
+// One thread per (output pixel, 4 consecutive patch entries): 32-bit index arithmetic (the 64-bit divisions of a
+// thread-per-element version cost more than the memory traffic) and one 16-byte store per thread.
+__global__ void __launch_bounds__(256)
+im2col_nchw_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int H, int W, int k, int stride, int pad,
+                   int OH, int OW, int k_pad, uint32_t total4) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total4) return;
+  const uint32_t quads = (uint32_t)k_pad >> 2;
+  const uint32_t pixel = t / quads, kq = t - pixel * quads;
+  const uint32_t ow = pixel % (uint32_t)OW, r = pixel / (uint32_t)OW;
+  const uint32_t oh = r % (uint32_t)OH, n = r / (uint32_t)OH;
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int kk = (int)kq * 4 + j;
+    v[j] = 0.f;
+    if (kk < k * k * C) {
+      const int c = kk % C, tap = kk / C;
+      const int ky = tap / k, kx = tap - ky * k;
+      const int iy = (int)oh * stride + ky - pad, ix = (int)ow * stride + kx - pad;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[j] = __ldg(src + (((size_t)n * C + c) * H + iy) * (size_t)W + ix);
+    }
   }
-  dst[e] = v;
+  *reinterpret_cast<float4 *>(dst + (size_t)pixel * k_pad + kq * 4) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 }  // namespace
@@ -248,8 +255,10 @@ extern "C" int pcodec_im2col_nchw(const float *src, float *dst, int batch, int c
                                   int stride, int pad, int out_h, int out_w, int k_pad, void *stream) {
   if (!src || !dst || batch <= 0 || channels <= 0 || k <= 0 || stride <= 0 || k_pad < k * k * channels)
     return PCODEC_ERR_BAD_ARG;
-  const int64_t total = (int64_t)batch * out_h * out_w * k_pad;
-  im2col_nchw_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
-      src, dst, channels, height, width, k, stride, pad, out_h, out_w, k_pad, total);
+  if ((k_pad & 3) || (reinterpret_cast<uintptr_t>(dst) & 15)) return PCODEC_ERR_BAD_ARG;
+  const int64_t total4 = (int64_t)batch * out_h * out_w * (k_pad / 4);
+  if (total4 >= (1ll << 32)) return PCODEC_ERR_UNSUPPORTED;
+  im2col_nchw_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, as_stream(stream)>>>(
+      src, dst, channels, height, width, k, stride, pad, out_h, out_w, k_pad, (uint32_t)total4);
   PCODEC_RETURN_LAUNCH();
 }
