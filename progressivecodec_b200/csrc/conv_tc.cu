@@ -258,6 +258,42 @@ __device__ __noinline__ float4 tc_epilogue4(int epi, float4 v, float4 r1, float4
   return o;
 }
 
+// Eight values (two float4 of two tile rows) per call: twice the independent chains per warp for the latency-bound
+// epilogue warps.
+struct F8 { float4 a, b; };
+__device__ __noinline__ F8 tc_epilogue8(int epi, F8 v, F8 r1, F8 r2, bool has_r2) {
+#define PC_EACH8(expr)                                                                          \
+  do {                                                                                         \
+    { const float a = v.a.x, p = r1.a.x, q = r2.a.x; (void)p; (void)q; o.a.x = (expr); }        \
+    { const float a = v.b.x, p = r1.b.x, q = r2.b.x; (void)p; (void)q; o.b.x = (expr); }        \
+    { const float a = v.a.y, p = r1.a.y, q = r2.a.y; (void)p; (void)q; o.a.y = (expr); }        \
+    { const float a = v.b.y, p = r1.b.y, q = r2.b.y; (void)p; (void)q; o.b.y = (expr); }        \
+    { const float a = v.a.z, p = r1.a.z, q = r2.a.z; (void)p; (void)q; o.a.z = (expr); }        \
+    { const float a = v.b.z, p = r1.b.z, q = r2.b.z; (void)p; (void)q; o.b.z = (expr); }        \
+    { const float a = v.a.w, p = r1.a.w, q = r2.a.w; (void)p; (void)q; o.a.w = (expr); }        \
+    { const float a = v.b.w, p = r1.b.w, q = r2.b.w; (void)p; (void)q; o.b.w = (expr); }        \
+  } while (0)
+  F8 o;
+  switch (epi) {
+    case PCODEC_EPI_GELU: PC_EACH8(gelu_erf(a)); break;
+    case PCODEC_EPI_ADD: PC_EACH8(a + p); break;
+    case PCODEC_EPI_ADD_GELU: PC_EACH8(gelu_erf(a + p)); break;
+    case PCODEC_EPI_GATE: PC_EACH8(q * sigmoid_f(a) + p); break;
+    case PCODEC_EPI_GDN: PC_EACH8(p * rsqrtf(a)); break;
+    case PCODEC_EPI_IGDN: PC_EACH8(p * sqrtf(a)); break;
+    case PCODEC_EPI_LRP:
+      if (has_r2) PC_EACH8(__fadd_rn(__fadd_rn(p, __fmul_rn(0.5f, tanhf(a))), q));
+      else PC_EACH8(__fadd_rn(p, __fmul_rn(0.5f, tanhf(a))));
+      break;
+    case PCODEC_EPI_CLAMP01: PC_EACH8(fminf(fmaxf(a, 0.f), 1.f)); break;
+    case PCODEC_EPI_LEAKY: PC_EACH8(a > 0.f ? a : __fmul_rn(0.01f, a)); break;
+    case PCODEC_EPI_LEAKY_ADD: PC_EACH8((a > 0.f ? a : __fmul_rn(0.01f, a)) + p); break;
+    default: o = v; break;
+  }
+#undef PC_EACH8
+  return o;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -601,19 +637,26 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         const int co = n0 + c0 + 4 * cc;
         const float4 bias4 = d.bias ? __ldg(reinterpret_cast<const float4 *>(d.bias + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = i * 8 + rl;
-          const float4 v = *reinterpret_cast<const float4 *>(stg + r * 64 + (((uint32_t)cc ^ ((uint32_t)(r >> 1) & 3u)) << 4));
-          if (!((ok_t >> i) & 1u)) continue;
-          const float4 a1 = d.r1 ? __ldg(reinterpret_cast<const float4 *>(d.r1 + opix_t[i] * d.r1_pixel_stride + co))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 a2 = d.r2 ? __ldg(reinterpret_cast<const float4 *>(d.r2 + opix_t[i] * d.r2_pixel_stride + co))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (threadIdx.x == 0 && c0 == 0 && i == 0 && v.x != 123.f) TC_TRACE_G(10);
-          const float4 o = tc_epilogue4(d.epilogue, make_float4(v.x + bias4.x, v.y + bias4.y, v.z + bias4.z, v.w + bias4.w),
-                                        a1, a2, has_r2);
-          if (threadIdx.x == 0 && c0 == 0 && i == 0 && o.x != 123.f) TC_TRACE_G(11);
-          *reinterpret_cast<float4 *>(d.out + opix_t[i] * d.out_pixel_stride + co) = o;
+        for (int i = 0; i < 4; i += 2) {  // two tile rows (i, i + 1) per call
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          F8 v, a1, a2;
+          {
+            const int r0 = i * 8 + rl, r1_ = (i + 1) * 8 + rl;
+            v.a = *reinterpret_cast<const float4 *>(stg + r0 * 64 + (((uint32_t)cc ^ ((uint32_t)(r0 >> 1) & 3u)) << 4));
+            v.b = *reinterpret_cast<const float4 *>(stg + r1_ * 64 + (((uint32_t)cc ^ ((uint32_t)(r1_ >> 1) & 3u)) << 4));
+          }
+          const bool ok0 = (ok_t >> i) & 1u, ok1 = (ok_t >> (i + 1)) & 1u;
+          a1.a = (d.r1 && ok0) ? __ldg(reinterpret_cast<const float4 *>(d.r1 + opix_t[i] * d.r1_pixel_stride + co)) : z4;
+          a1.b = (d.r1 && ok1) ? __ldg(reinterpret_cast<const float4 *>(d.r1 + opix_t[i + 1] * d.r1_pixel_stride + co)) : z4;
+          a2.a = (d.r2 && ok0) ? __ldg(reinterpret_cast<const float4 *>(d.r2 + opix_t[i] * d.r2_pixel_stride + co)) : z4;
+          a2.b = (d.r2 && ok1) ? __ldg(reinterpret_cast<const float4 *>(d.r2 + opix_t[i + 1] * d.r2_pixel_stride + co)) : z4;
+          v.a = make_float4(v.a.x + bias4.x, v.a.y + bias4.y, v.a.z + bias4.z, v.a.w + bias4.w);
+          v.b = make_float4(v.b.x + bias4.x, v.b.y + bias4.y, v.b.z + bias4.z, v.b.w + bias4.w);
+          if (threadIdx.x == 0 && c0 == 0 && i == 0) TC_TRACE_G(10);
+          const F8 o = tc_epilogue8(d.epilogue, v, a1, a2, has_r2);
+          if (threadIdx.x == 0 && c0 == 0 && i == 0 && o.a.x != 123.f) TC_TRACE_G(11);
+          if (ok0) *reinterpret_cast<float4 *>(d.out + opix_t[i] * d.out_pixel_stride + co) = o.a;
+          if (ok1) *reinterpret_cast<float4 *>(d.out + opix_t[i + 1] * d.out_pixel_stride + co) = o.b;
           if (threadIdx.x == 0 && c0 == 0 && i == 0) TC_TRACE_G(7);
         }
         if (threadIdx.x == 0 && c0 == 0) TC_TRACE_G(8);
