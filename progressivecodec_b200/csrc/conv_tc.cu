@@ -196,6 +196,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Asynchronous form: the registers are valid after tmem_wait_ld(); tmem_pin() keeps the compiler from moving their
+// uses in front of that wait.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_pin(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+
 // SWIZZLE_128B, K-major, 8-row x 128-byte atoms stacked along M/N with a 1024-byte stride (SM100 descriptor v1)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -615,12 +630,49 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
       }
       const uint32_t wr_off = (uint32_t)lane * 64u, wr_x = (uint32_t)(lane >> 1) & 3u;
       if (threadIdx.x == 0) TC_TRACE_G(9);
+      auto load_bias = [&](int c0) {
+        const int co = n0 + c0 + 4 * cc;
+        return (d.bias && co < d.cout) ? __ldg(reinterpret_cast<const float4 *>(d.bias + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      const bool two = n_acc > 1 && ((acc_mask >> 1) & 1u);
       for (int c0 = third * 16; c0 < bn; c0 += 16 * (TC_PRODUCER_WARPS / 4)) {
         if (n0 + c0 >= d.cout) break;  // padded last N tile
+        const int co = n0 + c0 + 4 * cc;
+        // What does not depend on the accumulators first: the bias and the first pass's residual values (L2 hits,
+        // prefetched at kernel start) are in flight while tensor memory is read, the second pass's during the first.
+        float4 bias4;
+        if (NG == 2) bias4 = load_bias(c0);
+        auto load_res1 = [&](int i) {
+          return (d.r1 && ((ok_t >> i) & 1u)) ? __ldg(reinterpret_cast<const float4 *>(d.r1 + opix_t[i] * d.r1_pixel_stride + co))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        const float4 z4_ = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 ra0 = NG == 2 ? load_res1(0) : z4_, ra1 = NG == 2 ? load_res1(1) : z4_;  // (NG == 1: no registers to spare)
         float acc[16];
-        tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective
+        if (NG == 1) {
+          tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective
+          if (two) {
+            float part[16];
+            tmem_ld16(lane_addr + (uint32_t)(bn + c0), part);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] += part[j];
+          }
+        } else {  // two accumulators per wait
+          uint32_t t0[16], t1[16];
+          tmem_ld16_issue(lane_addr + (uint32_t)c0, t0);
+          if (two) tmem_ld16_issue(lane_addr + (uint32_t)(bn + c0), t1);
+          tmem_wait_ld();
+          tmem_pin(t0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(t0[j]);
+          if (two) {
+            tmem_pin(t1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(t1[j]);
+          }
+        }
 #pragma unroll 1
-        for (int a = 1; a < n_acc; ++a) {
+        for (int a = 2; a < n_acc; ++a) {
           if (!((acc_mask >> a) & 1u)) continue;
           float part[16];
           tmem_ld16(lane_addr + (uint32_t)(a * bn + c0), part);
@@ -634,8 +686,8 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
               make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
         __syncwarp();
         if (threadIdx.x == 0 && c0 == 0) TC_TRACE_G(6);
-        const int co = n0 + c0 + 4 * cc;
-        const float4 bias4 = d.bias ? __ldg(reinterpret_cast<const float4 *>(d.bias + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NG == 1) bias4 = load_bias(c0);
+        const float4 rb0 = NG == 2 ? load_res1(2) : z4_, rb1 = NG == 2 ? load_res1(3) : z4_;
 #pragma unroll
         for (int i = 0; i < 4; i += 2) {  // two tile rows (i, i + 1) per call
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -646,8 +698,8 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
             v.b = *reinterpret_cast<const float4 *>(stg + r1_ * 64 + (((uint32_t)cc ^ ((uint32_t)(r1_ >> 1) & 3u)) << 4));
           }
           const bool ok0 = (ok_t >> i) & 1u, ok1 = (ok_t >> (i + 1)) & 1u;
-          a1.a = (d.r1 && ok0) ? __ldg(reinterpret_cast<const float4 *>(d.r1 + opix_t[i] * d.r1_pixel_stride + co)) : z4;
-          a1.b = (d.r1 && ok1) ? __ldg(reinterpret_cast<const float4 *>(d.r1 + opix_t[i + 1] * d.r1_pixel_stride + co)) : z4;
+          a1.a = NG == 2 ? (i == 0 ? ra0 : rb0) : load_res1(i);
+          a1.b = NG == 2 ? (i == 0 ? ra1 : rb1) : load_res1(i + 1);
           a2.a = (d.r2 && ok0) ? __ldg(reinterpret_cast<const float4 *>(d.r2 + opix_t[i] * d.r2_pixel_stride + co)) : z4;
           a2.b = (d.r2 && ok1) ? __ldg(reinterpret_cast<const float4 *>(d.r2 + opix_t[i + 1] * d.r2_pixel_stride + co)) : z4;
           v.a = make_float4(v.a.x + bias4.x, v.a.y + bias4.y, v.a.z + bias4.z, v.a.w + bias4.w);
