@@ -98,7 +98,6 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t m, uint32_t magic, int shi
   return (uint32_t)(((uint64_t)m * magic) >> (31 + shift));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -220,25 +219,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                       // layout type: SWIZZLE_128B
   return d;
-}
-
-__device__ __forceinline__ float tc_epilogue(int epi, float acc, float r1, float r2, bool has_r2) {
-  switch (epi) {
-    case PCODEC_EPI_GELU: return gelu_erf(acc);
-    case PCODEC_EPI_ADD: return acc + r1;
-    case PCODEC_EPI_ADD_GELU: return gelu_erf(acc + r1);
-    case PCODEC_EPI_GATE: return r2 * sigmoid_f(acc) + r1;
-    case PCODEC_EPI_GDN: return r1 * rsqrtf(acc);
-    case PCODEC_EPI_IGDN: return r1 * sqrtf(acc);
-    case PCODEC_EPI_LRP: {
-      float v = __fadd_rn(r1, __fmul_rn(0.5f, tanhf(acc)));
-      return has_r2 ? __fadd_rn(v, r2) : v;
-    }
-    case PCODEC_EPI_CLAMP01: return fminf(fmaxf(acc, 0.f), 1.f);
-    case PCODEC_EPI_LEAKY: return acc > 0.f ? acc : __fmul_rn(0.01f, acc);
-    case PCODEC_EPI_LEAKY_ADD: return (acc > 0.f ? acc : __fmul_rn(0.01f, acc)) + r1;
-    default: return acc;
-  }
 }
 
 // Four channels at once behind ONE switch: keeps a single copy of every transcendental in the kernel image (the code is
