@@ -890,7 +890,10 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
   const bool short_1tap = n_taps == 1 && n_slabs <= 24;
   bool small = mode < 0 ? (short_1tap && cout <= 128) : ((mode >= 1 && cout <= 64) || (mode >= 2 && short_1tap));
   const bool shared = small && short_1tap && (mode < 0 || mode >= 3);
-  const int bn = small ? pick_bn(cout, n_taps * cin_total, shared ? 128 : 64, shared ? 256 + 128 : 256)
+  // mode 4: tiles of up to 192 columns in the two-CTA variant (192 accumulator columns + ONE 64-column A buffer = 256,
+  // one pipeline stage): the main loop is serialised, but it is short and hides behind the other CTA's epilogue.
+  const bool wide = shared && mode == 4;
+  const int bn = small ? pick_bn(cout, n_taps * cin_total, wide ? 192 : (shared ? 128 : 64), wide ? 512 : (shared ? 256 + 128 : 256))
                        : pick_bn(cout, n_taps * cin_total);
   if (bn == 0 || (cin_total % 4) != 0) return PCODEC_ERR_UNSUPPORTED;
   EncodeTiledFn enc = get_encode_fn();
@@ -984,7 +987,7 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   auto need = [&](int st) { return std::max(st * stage_bytes, 12 * 2048) + 1024 + 8 * (4 * st + 6) + 64; };
   const int smem_limit = h->small ? 110 * 1024 : TC_SMEM_LIMIT;
   const int tmem_limit = h->small ? 256 : 512;
-  int stages = 2;
+  int stages = 1;
   while (need(stages + 1) <= smem_limit && stages < 8) ++stages;
   if (const char *e = getenv("PCODEC_TC_STAGES")) stages = std::min(stages, atoi(e));  // experiment knob
   if (stages > n_steps) stages = n_steps;
@@ -1011,6 +1014,7 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
     if (h->small == 2) {  // single shared accumulator
       P.shared_lo = 1;
       n_acc = 1 + (split3 ? 1 : 0);
+      if (h->bn + ring * a_cols > tmem_limit) ring = 1;
     }
     int n_hi = n_acc - (split3 ? 1 : 0);
     if (n_hi > 4) n_hi = 4;
