@@ -5,6 +5,9 @@
 Base net = authors' flags with synthetic weights (as the other goldens); the 3 x 10 LatentRateReduction nets get
 name-keyed synthetic weights too (`apply_synthetic_weights(rem.post_latent)`, names relative to post_latent).
 Levels: 0, one per refinement interval (0.1 in (0.01, 0.25], 1 in (0.25, 1.75], 5 above), and the top level 10.
+`rem_escalation.npz`: the ``checkpoint_rep`` path (CHProgREM.py:338-372, :773, :989) — the reference's own
+``extract_chekpoint_representation_from_images`` with ``escalation=True`` chained over the three check levels, then one
+compress + decompress at quality 5 on top of the last representation.
 """
 from __future__ import annotations
 
@@ -53,6 +56,52 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     run("rem", REM_KW, REM_QUALITIES, 55, a.check)
     run("rem_mustd", REM_KW2, REM_QUALITIES2, 56, a.check)
+    run_escalation(a.check)
+
+
+def run_escalation(check):
+    kwargs, shape = CASES["authors"]
+    rem_kw = dict(REM_KW, escalation=True)
+    rem = build_reference_rem(kwargs, rem_kw)
+    x = synthetic_image(shape, seed=57)
+    rec = {"x": x.numpy()}
+    with torch.no_grad():
+        out = io.StringIO()
+        stdout, sys.stdout = sys.stdout, out
+        try:
+            reps = [rem.extract_chekpoint_representation_from_images(x, q) for q in rem_kw["check_levels"]]
+        finally:
+            sys.stdout = stdout
+        for k, r in enumerate(reps):
+            rec[f"rep{k}"] = r.numpy()
+        c = rem.compress(x, quality=5, mask_pol="point-based-std", checkpoint_rep=reps[-1])
+        d = rem.decompress(c["strings"], c["shape"], quality=5, mask_pol="point-based-std", checkpoint_rep=reps[-1])
+        for k, v in pack_strings(c["strings"]).items():
+            rec["q5_" + k] = v
+        rec["q5_shape"] = np.array(list(c["shape"]), dtype=np.int64)
+        rec["q5_x_hat"] = d["x_hat"].numpy()
+        rec["q5_y_hat"] = c["y_hat"].numpy()
+    path = os.path.join(GOLD, "rem_escalation.npz")
+    np.savez_compressed(path, **rec)
+    print(f"[golden] rem_escalation: {os.path.getsize(path) / 1024:.0f} KiB")
+    if check:
+        from .codec_port import CodecConfig
+        from .rem_port import OracleREM
+
+        orc = OracleREM(rem.base_net.state_dict(), rem.post_latent.state_dict(), CodecConfig(**kwargs), **REM_KW)
+        cl = REM_KW["check_levels"]
+        r = orc.compress(x, quality=cl[0], mask_pol="point-based-std")["y_hat"]
+        errs = [float(np.abs(r.numpy() - rec["rep0"]).max())]
+        for k in (1, 2):
+            r = orc.compress(x, quality=cl[k], mask_pol="point-based-std", checkpoint_rep=r)["y_hat"]
+            errs.append(float(np.abs(r.numpy() - rec[f"rep{k}"]).max()))
+        c = orc.compress(x, quality=5, mask_pol="point-based-std", checkpoint_rep=torch.from_numpy(rec["rep2"]))
+        ref = unpack_strings(rec, "q5_")
+        same = c["strings"][0] == ref[0] and c["strings"][1] == ref[1]
+        d = orc.decompress(ref, tuple(rec["q5_shape"]), quality=5, mask_pol="point-based-std",
+                           checkpoint_rep=torch.from_numpy(rec["rep2"]))
+        print(f"   escalation: rep max|d|={errs}, strings identical={same}, "
+              f"x_hat max|d|={float(np.abs(d['x_hat'].numpy() - rec['q5_x_hat']).max()):.3g}")
 
 
 def run(name, rem_kw, qualities, seed, check):

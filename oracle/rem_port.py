@@ -85,12 +85,14 @@ class OracleREM(OracleCodec):
         return mu, enh
 
     # -- shared progressive loop ----------------------------------------------------------------------------
-    def _rem_prog(self, lm, ls, y_hat_base, mu_base, std_base, quality, mask_pol, code):
+    def _rem_prog(self, lm, ls, y_hat_base, mu_base, std_base, quality, mask_pol, code, checkpoint_rep=None):
         c = self.cfg
         d0 = c.division_dimension[0]
         y_hat_q: List[Tensor] = []
         mu_total: List[Tensor] = []
         std_total: List[Tensor] = []
+        # CHProgREM.py:773 / :989: the refinement nets read the decoded check-level representation when one is given
+        y_b_hats = list(checkpoint_rep.chunk(self.ns0, 1)) if checkpoint_rep is not None else y_hat_base
         for i in range(self.ns1 - self.ns0):
             sv_mean = mu_total if c.all_scalable else y_hat_q
             sv_std = std_total if c.all_scalable else y_hat_q
@@ -104,7 +106,7 @@ class OracleREM(OracleCodec):
             mu_scale_base = torch.cat([mu_base[i], std_base[i]], 1)
             mu_scale_enh = torch.cat([mu, scale], 1) if self.mu_std else scale
             q_bar, _q_post = self.find_check_quality(quality)
-            mu, scale = self.apply_latent_enhancement(i, quality, q_bar, y_hat_base[i], mu_scale_base, mu_scale_enh, mu,
+            mu, scale = self.apply_latent_enhancement(i, quality, q_bar, y_b_hats[i], mu_scale_base, mu_scale_enh, mu,
                                                       scale, mask_pol)
             m = self.mask(scale, quality, mask_pol)
             y_hat = code(i, mu, scale, m)
@@ -133,7 +135,8 @@ class OracleREM(OracleCodec):
         return y_hat_base, mu_base, std_base
 
     @torch.no_grad()
-    def compress(self, x: Tensor, quality=0.0, mask_pol: Optional[str] = "point-based-std", coder=None, debug=None):
+    def compress(self, x: Tensor, quality=0.0, mask_pol: Optional[str] = "point-based-std", coder=None, debug=None,
+                 checkpoint_rep: Optional[Tensor] = None):
         c = self.cfg
         coder = coder or EP.default_coder()
         y = self.g_a(x)
@@ -173,13 +176,14 @@ class OracleREM(OracleCodec):
             dbg_idx.append(idx)
             return sym.float() + mu
 
-        y_hat_q = self._rem_prog(lm, ls, y_hat_base, mu_base, std_base, quality, mask_pol, code_prog)
+        y_hat_q = self._rem_prog(lm, ls, y_hat_base, mu_base, std_base, quality, mask_pol, code_prog, checkpoint_rep)
         if debug is not None:
             debug.update(symbols=dbg_sym, indexes=dbg_idx, z_sym=z_sym)
         return {"strings": [y_strings, z_strings], "shape": z.shape[-2:], "masks": masks, "y_hat": torch.cat(y_hat_q, 1)}
 
     @torch.no_grad()
-    def decompress(self, strings, shape, quality, mask_pol: Optional[str] = None, coder=None):
+    def decompress(self, strings, shape, quality, mask_pol: Optional[str] = None, coder=None,
+                   checkpoint_rep: Optional[Tensor] = None):
         c = self.cfg
         coder = coder or EP.default_coder()
         mask_pol = c.mask_policy if mask_pol is None else mask_pol
@@ -199,6 +203,6 @@ class OracleREM(OracleCodec):
             idx = self.gc.build_indexes(scale * m)
             return self.gc.decode(y_strings[self.ns0 + i], idx, coder).float() + mu
 
-        y_hat_q = self._rem_prog(lm, ls, y_hat_base, mu_base, std_base, quality, mask_pol, code_prog)
+        y_hat_q = self._rem_prog(lm, ls, y_hat_base, mu_base, std_base, quality, mask_pol, code_prog, checkpoint_rep)
         y_hat_en = torch.cat(y_hat_q, 1)
         return {"x_hat": self.g_s(y_hat_en, 1).clamp_(0, 1), "y_hat": y_hat_en}

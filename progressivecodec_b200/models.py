@@ -675,7 +675,7 @@ class ChannelProgresssiveWACNN(nn.Module):
 
     @torch.no_grad()
     def compress(self, x, quality=0.0, mask_pol=None, cust_map=None, return_device_streams: bool = False,
-                 debug: Optional[dict] = None, _rem=None):
+                 debug: Optional[dict] = None, _rem=None, _rem_ckpt=None):
         """CHProg_cnn.py:686-847.  One batched rANS launch codes every (slice, image) stream.
         `debug` (tests only) receives the device symbol / index planes [n_slices, B, 32*h*w] and z symbols."""
         mask_pol = self.mask_policy if mask_pol is None else mask_pol
@@ -708,7 +708,9 @@ class ChannelProgresssiveWACNN(nn.Module):
 
             refine = None
             if _rem is not None:
-                refine = lambda i, mu, scale, base_i: _rem._refine(E, quality, mask_pol, i, mu, scale, base_i, record)
+                ck = self._checkpoint_act(E, _rem_ckpt, B, h, w)  # CHProgREM.py:773: y_b_hats = checkpoint_rep.chunk(10, 1)
+                refine = lambda i, mu, scale, base_i: _rem._refine(
+                    E, quality, mask_pol, i, mu, scale, base_i if ck is None else ck.slice(32 * i, 32), record)
             y_hat_out = self._prog_slices(P, lm, ls, y_hat_base, quality, mask_pol, code_prog, "codec",
                                           cust_map=self._cust_map_act(E, cust_map, B, h, w), refine=refine)
         if debug is not None:
@@ -724,7 +726,8 @@ class ChannelProgresssiveWACNN(nn.Module):
         return {"strings": [y_strings, _ans.split_streams(z_data, z_off)], "shape": shape, "masks": masks, **extra}
 
     @torch.no_grad()
-    def decompress(self, strings, shape, quality, mask_pol=None, cust_map=None, _worker: int = 0, _rem=None):
+    def decompress(self, strings, shape, quality, mask_pol=None, cust_map=None, _worker: int = 0, _rem=None,
+                   _rem_ckpt=None):
         """CHProg_cnn.py:849-999.
 
         `_worker` (not part of the reference API) gives concurrent decompress() calls from different host threads their
@@ -752,7 +755,7 @@ class ChannelProgresssiveWACNN(nn.Module):
         if groups == 1:
             # slot 1, not 0: slot 0 belongs to the encoder-side entry points, which pipeline.sweep() runs concurrently
             out = self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, 0, B, shape, quality, mask_pol,
-                                         slot=1 + 8 * _worker, cust_map=cust_map, rem=_rem)
+                                         slot=1 + 8 * _worker, cust_map=cust_map, rem=_rem, rem_ckpt=_rem_ckpt)
             return {"x_hat": out[0], "y_hat": out[1]} if _rem is not None else {"x_hat": out}
         import threading
 
@@ -778,7 +781,8 @@ class ChannelProgresssiveWACNN(nn.Module):
                     outs[g] = self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, lo, hi, shape,
                                                      quality, mask_pol, slot=g + 1 + 8 * _worker,
                                                      cust_map=cust_map[lo:hi] if cust_map is not None else None,
-                                                     rem=_rem)
+                                                     rem=_rem,
+                                                     rem_ckpt=_rem_ckpt[lo:hi] if _rem_ckpt is not None else None)
             except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
                 errs[g] = e
 
@@ -853,8 +857,18 @@ class ChannelProgresssiveWACNN(nn.Module):
             raise L.PcodecError("cust_map must be a CUDA tensor")
         return E.from_nchw(cust_map)
 
+    def _checkpoint_act(self, E: Engine, rep, B: int, h: int, w: int) -> Optional[Act]:
+        """REM ``checkpoint_rep`` [B, 32*ns0, h, w] (the ``y_hat`` of a compress()/decompress() at a check level) -> NHWC."""
+        if rep is None:
+            return None
+        if tuple(rep.shape) != (B, 32 * self.ns0, h, w):
+            raise ValueError(f"checkpoint_rep must have shape {(B, 32 * self.ns0, h, w)}, got {tuple(rep.shape)}")
+        if not rep.is_cuda:
+            raise L.PcodecError("checkpoint_rep must be a CUDA tensor")
+        return E.from_nchw(rep.float().contiguous())
+
     def _decompress_group(self, P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi, shape, quality, mask_pol,
-                          slot: int = 0, cust_map=None, rem=None):
+                          slot: int = 0, cust_map=None, rem=None, rem_ckpt=None):
         """Decode images [lo, hi) of a batch whose streams are laid out slice-major: stream (s, b) = s*B_total + b."""
         record: Optional[list] = [] if rem is not None else None
         lm, ls, y_hat_base, decode_slice = self._decode_base(P, y_data, y_off_dev, z_data, z_off_dev, B_total, lo, hi,
@@ -865,7 +879,9 @@ class ChannelProgresssiveWACNN(nn.Module):
             return (x_hat, E.to_nchw(y_hat_base)) if rem is not None else x_hat
         refine = None
         if rem is not None:
-            refine = lambda i, mu, scale, base_i: rem._refine(E, quality, mask_pol, i, mu, scale, base_i, record)
+            ck = self._checkpoint_act(E, rem_ckpt, lm.B, lm.H, lm.W)  # CHProgREM.py:989
+            refine = lambda i, mu, scale, base_i: rem._refine(
+                E, quality, mask_pol, i, mu, scale, base_i if ck is None else ck.slice(32 * i, 32), record)
         y_hat_q = self._prog_slices(
             P, lm, ls, y_hat_base, quality, mask_pol,
             lambda i, mu, scale, mask_mode, thr, y_pre, mask_src=None: decode_slice(self.ns0 + i, scale, mask_mode, thr, mu,

@@ -9,8 +9,9 @@ preceding check level.  It hooks into the base model's slice loops (``_base_slic
 so every conv runs through the same tap-GEMM kernels (LeakyReLU / LeakyReLU+add epilogues) and the gate is one small
 fused kernel (``pcodec_masked_residual``).
 
-Out of scope (raise): training-time ``forward``/``forward_latent``, ``checkpoint_rep`` / ``escalation`` (encoding on top of
-a previously decoded check-level representation), ``real_compress=False``.
+``checkpoint_rep`` (the refinement nets read a previously decoded check-level representation instead of the base
+slices, :773 / :989) and the ``escalation`` chain ``extract_chekpoint_representation_from_images`` (:336-372) are
+supported.  Out of scope (raise): training-time ``forward``/``forward_latent``, ``real_compress=False``.
 """
 from __future__ import annotations
 
@@ -153,30 +154,38 @@ class PostRateProcessedNetwork(nn.Module):
         raise L.PcodecError("PostRateProcessedNetwork.forward / forward_latent are training-time paths outside the B200 "
                             "inference hot path; use compress() / decompress()")
 
-    def _check(self, checkpoint_rep):
-        if checkpoint_rep is not None or self.escalation:
-            raise NotImplementedError("checkpoint_rep / escalation (coding on top of a decoded check-level representation) "
-                                      "is not implemented on the B200 path")
+    @torch.no_grad()
+    def extract_chekpoint_representation_from_images(self, x, quality, rc=True):
+        """CHProgREM.py:336-372 (the reference's spelling): the decoded latent at a check level; with ``escalation`` each
+        level is coded on top of the representation of the level below."""
+        if not self.escalation:
+            return self.compress(x, quality=quality, mask_pol="point-based-std", real_compress=rc)["y_hat"]
+        cl = self.check_levels
+        out = self.compress(x, quality=cl[0], mask_pol="point-based-std", real_compress=rc)["y_hat"]
+        if quality == cl[0]:
+            return out
+        out = self.compress(x, quality=cl[1], mask_pol="point-based-std", checkpoint_rep=out, real_compress=rc)["y_hat"]
+        if quality == cl[1]:
+            return out
+        return self.compress(x, quality=cl[2], mask_pol="point-based-std", checkpoint_rep=out, real_compress=rc)["y_hat"]
 
     @torch.no_grad()
     def compress(self, x, quality=0.0, mask_pol="point-based-std", checkpoint_rep=None, real_compress=True, used_qual=None,
                  debug: Optional[dict] = None):
         """CHProgREM.py:673-887 -> {"strings", "shape", "masks", "y_hat"}."""
-        self._check(checkpoint_rep)
         if not real_compress:
             raise NotImplementedError("real_compress=False (quantise without entropy coding) is a training-time path")
         self._prepare(self.base_net._device())  # pack the refinement nets on this thread, before any worker needs them
-        return self.base_net.compress(x, quality=quality, mask_pol=mask_pol, debug=debug, _rem=self)
+        return self.base_net.compress(x, quality=quality, mask_pol=mask_pol, debug=debug, _rem=self, _rem_ckpt=checkpoint_rep)
 
     @torch.no_grad()
     def decompress(self, strings, shape, quality, mask_pol=None, checkpoint_rep=None, timing=False, used_qual=None):
         """CHProgREM.py:896-1126 -> {"x_hat", "y_hat", "time"} (y_hat: list of base slices at quality 0, else a tensor)."""
-        self._check(checkpoint_rep)
         import time as _time
 
         self._prepare(self.base_net._device())
         t0 = _time.time()
-        out = self.base_net.decompress(strings, shape, quality, mask_pol=mask_pol, _rem=self)
+        out = self.base_net.decompress(strings, shape, quality, mask_pol=mask_pol, _rem=self, _rem_ckpt=checkpoint_rep)
         if timing:
             torch.cuda.synchronize()
         y_hat = list(out["y_hat"].chunk(self.base_net.ns0, 1)) if quality == 0 else out["y_hat"]

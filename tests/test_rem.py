@@ -112,5 +112,53 @@ def test_rem_gpu_vs_oracle_and_golden(name):
     r1 = rem.decompress([[s[:1] for s in ob["strings"][0]], ob["strings"][1][:1]], ob["shape"], quality=1,
                         mask_pol="point-based-std")["x_hat"]
     assert torch.equal(rb[0], r1[0]) and torch.equal(rb[8], r1[0])
-    with pytest.raises(NotImplementedError):
-        rem.compress(x.cuda(), quality=1, checkpoint_rep=out["y_hat"])
+    with pytest.raises(ValueError):
+        rem.compress(x.cuda(), quality=1, checkpoint_rep=out["y_hat"][:, :32])
+
+
+def test_rem_escalation_oracle_matches_reference_golden():
+    """checkpoint_rep path (CHProgREM.py:336-372, :773, :989): golden = the real reference with escalation=True."""
+    _rem, orc = build_rem()
+    G = load_golden("rem_escalation")
+    x = torch.from_numpy(G["x"])
+    cl = REM_KW["check_levels"]
+    r = orc.compress(x, quality=cl[0], mask_pol="point-based-std")["y_hat"]
+    assert torch.equal(r, torch.from_numpy(G["rep0"]))
+    r = orc.compress(x, quality=cl[1], mask_pol="point-based-std", checkpoint_rep=r)["y_hat"]
+    assert torch.equal(r, torch.from_numpy(G["rep1"]))
+    rep2 = torch.from_numpy(G["rep2"])
+    ref = unpack_strings(G, "q5_")
+    d = orc.decompress(ref, tuple(G["q5_shape"]), quality=5, mask_pol="point-based-std", checkpoint_rep=rep2)
+    assert torch.equal(d["x_hat"], torch.from_numpy(G["q5_x_hat"]))
+    # the representation matters: without it the same strings decode to something else
+    d0 = orc.decompress(ref, tuple(G["q5_shape"]), quality=5, mask_pol="point-based-std")
+    assert not torch.equal(d0["x_hat"], d["x_hat"])
+
+
+@pytest.mark.gpu
+def test_rem_escalation_gpu_vs_golden():
+    from progressivecodec_b200 import PostRateProcessedNetwork
+
+    rem0, orc = build_rem("cuda")
+    rem = PostRateProcessedNetwork(rem0.base_net, **dict(REM_KW, escalation=True)).eval()
+    rem.post_latent.load_state_dict(rem0.post_latent.state_dict())
+    rem = rem.cuda()
+    G = load_golden("rem_escalation")
+    x = torch.from_numpy(G["x"])
+    cl = REM_KW["check_levels"]
+    npx = x.shape[0] * x.shape[2] * x.shape[3]
+    for k, q in enumerate(cl):  # the chained representations: latents agree with the reference's up to rounding-tie flips
+        r = rem.extract_chekpoint_representation_from_images(x.cuda(), q).cpu()
+        ref = torch.from_numpy(G[f"rep{k}"])
+        assert r.shape == ref.shape
+        assert float(((r - ref).abs() > 0.5).float().mean()) <= 1e-3, (q, float((r - ref).abs().max()))
+    rep2 = torch.from_numpy(G["rep2"]).cuda()
+    out = rem.compress(x.cuda(), quality=5, mask_pol="point-based-std", checkpoint_rep=rep2)
+    ref = unpack_strings(G, "q5_")
+    assert abs(bpp_from_strings(out["strings"], npx) - bpp_from_strings(ref, npx)) <= 0.005 * bpp_from_strings(ref, npx)
+    dec = rem.decompress(out["strings"], out["shape"], quality=5, mask_pol="point-based-std", checkpoint_rep=rep2)
+    assert abs(psnr(dec["x_hat"].cpu(), x) - psnr(torch.from_numpy(G["q5_x_hat"]), x)) <= 0.02
+    assert torch.equal(dec["y_hat"], out["y_hat"])
+    # and the representation is really used
+    d0 = rem.decompress(out["strings"], out["shape"], quality=5, mask_pol="point-based-std")
+    assert not torch.equal(d0["x_hat"], dec["x_hat"])
