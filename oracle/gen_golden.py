@@ -207,6 +207,42 @@ def run_custmap(check: bool):
             print(f"   custmap q={q}: strings identical={same}, x_hat max|d|={err:.3g}")
 
 
+def run_table800(check: bool):
+    """The 800-level scale table the reference defines but does not use (CHProg_cnn.py:16-26: 0.04 .. 256, 800 levels)
+    passed to ``update(scale_table=...)``; authors' flags, two levels.  -> tests/golden/authors_table800.npz"""
+    kwargs, shape = CASES["authors"]
+    net = build_reference(kwargs)
+    from compress.models.CHProg_cnn import get_scale_table as table800  # type: ignore
+
+    net.update(scale_table=table800(), force=True)
+    x = synthetic_image(shape, seed=78)
+    rec = {"x": x.numpy(), "scale_table": table800().numpy()}
+    qs = [0, 5]
+    with torch.no_grad():
+        for q in qs:
+            c = net.compress(x, quality=q, mask_pol="point-based-std")
+            d = net.decompress(c["strings"], c["shape"], quality=q, mask_pol="point-based-std")
+            tag = f"q{q}_"
+            for k, v in pack_strings(c["strings"]).items():
+                rec[tag + k] = v
+            rec[tag + "shape"] = np.array(list(c["shape"]), dtype=np.int64)
+            rec[tag + "x_hat"] = d["x_hat"].numpy()
+    path = os.path.join(GOLD, "authors_table800.npz")
+    np.savez_compressed(path, **rec)
+    print(f"[golden] authors_table800: {os.path.getsize(path) / 1024:.0f} KiB")
+    if check:
+        from .codec_port import CodecConfig, OracleCodec
+
+        orc = OracleCodec(net.state_dict(), CodecConfig(**kwargs))
+        for q in qs:
+            c = orc.compress(x, quality=q, mask_pol="point-based-std")
+            ref = unpack_strings(rec, f"q{q}_")
+            same = c["strings"][0] == ref[0] and c["strings"][1] == ref[1]
+            d = orc.decompress(ref, tuple(rec[f"q{q}_shape"]), quality=q, mask_pol="point-based-std")
+            err = float(np.abs(d["x_hat"].numpy() - rec[f"q{q}_x_hat"]).max())
+            print(f"   table800 q={q}: strings identical={same}, x_hat max|d|={err:.3g}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -216,6 +252,8 @@ def main():
     for name in a.cases:
         if name == "custmap":
             run_custmap(a.check)
+        elif name == "table800":
+            run_table800(a.check)
         else:
             run_case(name, a.check)
 

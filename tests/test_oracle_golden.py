@@ -115,3 +115,33 @@ def test_cust_map_masks_match_reference():
         ref_x = torch.from_numpy(G[f"q{q}_x_hat"])
         if not torch.equal(rec, ref_x):
             assert abs(psnr(rec, x) - psnr(ref_x, x)) <= 0.02
+
+
+def build_table800_pair(device=None):
+    """Authors' flags with the reference's 800-level scale table (CHProg_cnn.py:16-26) passed to update()."""
+    from conftest import CASE_KWARGS
+    from oracle.codec_port import CodecConfig, OracleCodec
+    from progressivecodec_b200 import ChannelProgresssiveWACNN, apply_synthetic_weights, get_scale_table
+
+    kw = CASE_KWARGS["authors"]
+    net = ChannelProgresssiveWACNN(**kw).eval()
+    apply_synthetic_weights(net, seed=0)
+    net.update(scale_table=get_scale_table(0.04, 256, 800), force=True)
+    orc = OracleCodec(net.state_dict(), CodecConfig(**kw))
+    return (net.to(device) if device is not None else net), orc
+
+
+def test_800_level_scale_table_matches_reference():
+    """update(scale_table=<800 levels>) (the table CHProg_cnn.py:16-26 defines): our table construction + the oracle
+    reproduce the real reference's streams (tests/golden/authors_table800.npz, oracle/gen_golden.py --cases table800)."""
+    net, orc = build_table800_pair()
+    G = load_golden("authors_table800")
+    assert np.array_equal(net.gaussian_conditional.scale_table.numpy(), G["scale_table"])
+    assert tuple(net.gaussian_conditional._quantized_cdf.shape)[0] == 800
+    x = torch.from_numpy(G["x"])
+    for q in (0, 5):
+        ref = unpack_strings(G, f"q{q}_")
+        out = orc.compress(x, quality=q, mask_pol="point-based-std")
+        assert out["strings"][0] == ref[0] and out["strings"][1] == ref[1], q
+        rec = orc.decompress(ref, tuple(G[f"q{q}_shape"]), quality=q, mask_pol="point-based-std")["x_hat"]
+        assert torch.equal(rec, torch.from_numpy(G[f"q{q}_x_hat"])), q
