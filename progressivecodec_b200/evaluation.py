@@ -85,6 +85,29 @@ def read_image(path: str) -> Tensor:
     return torch.from_numpy(img).permute(2, 0, 1).contiguous()
 
 
+class TestKodakDataset(torch.utils.data.Dataset):
+    """datasets/utils.py:58-74: every file of `data_dir` as (transform(RGB image), path) — Kodak / CLIC test folders."""
+
+    def __init__(self, data_dir: str, transform=None):
+        if not os.path.exists(data_dir):
+            raise Exception(f"[!] {data_dir} not exitd")  # (the reference's message)
+        self.data_dir = data_dir
+        self.transform = transform
+        self.image_path = [os.path.join(data_dir, f) for f in sorted(os.listdir(data_dir))]
+
+    def __getitem__(self, item):
+        from PIL import Image
+
+        path = self.image_path[item]
+        image = Image.open(path).convert("RGB")
+        if self.transform is None:
+            return read_image(path), path
+        return self.transform(image), path
+
+    def __len__(self):
+        return len(self.image_path)
+
+
 class AverageMeter:
     """utils/functions.py AverageMeter."""
 

@@ -211,3 +211,36 @@ def test_load_checkpoint_round_trip_cpu_side():
         assert k1 == k2 and (v1.shape == v2.shape)
         if v1.dtype.is_floating_point and "quantized_cdf" not in k1:
             assert (v1 == v2).all(), k1
+
+
+def test_eval_helpers_dataset_padding_metrics(tmp_path):
+    """Host side of the evaluation harness (datasets/utils.py:58-74, training/step.py compute_padding / psnr)."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from progressivecodec_b200 import evaluation as ev
+
+    rng = np.random.default_rng(0)
+    for k, (h, w) in enumerate([(40, 72), (33, 50)]):
+        Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(tmp_path / f"img{k}.png")
+    ds = ev.TestKodakDataset(str(tmp_path))
+    assert len(ds) == 2
+    x, path = ds[1]
+    assert path.endswith("img1.png") and tuple(x.shape) == (3, 33, 50) and 0.0 <= float(x.min()) and float(x.max()) <= 1.0
+    assert torch.equal(x, ev.read_image(path))
+    with pytest.raises(Exception):
+        ev.TestKodakDataset(str(tmp_path / "missing"))
+    pad, unpad = ev.compute_padding(33, 50, min_div=64)
+    xp = torch.nn.functional.pad(x.unsqueeze(0), pad)
+    assert xp.shape[2] % 64 == 0 and xp.shape[3] % 64 == 0
+    assert torch.equal(torch.nn.functional.pad(xp, unpad), x.unsqueeze(0))
+    with pytest.raises(ValueError):  # log10(0), exactly like training/step.py:13-15
+        ev.compute_psnr(x, x)
+    y = (x + 0.1).clamp(0, 1)
+    mse = float(((x - y) ** 2).mean())
+    assert abs(ev.compute_psnr(x, y) - (-10 * np.log10(mse))) < 1e-4
+    m = ev.AverageMeter()
+    m.update(2.0)
+    m.update(4.0, n=3)
+    assert m.count == 4 and abs(m.avg - 3.5) < 1e-12
