@@ -675,7 +675,7 @@ class ChannelProgresssiveWACNN(nn.Module):
 
     @torch.no_grad()
     def compress(self, x, quality=0.0, mask_pol=None, cust_map=None, return_device_streams: bool = False,
-                 debug: Optional[dict] = None, _rem=None, _rem_ckpt=None):
+                 debug: Optional[dict] = None, _rem=None, _rem_ckpt=None, _no_entropy: bool = False):
         """CHProg_cnn.py:686-847.  One batched rANS launch codes every (slice, image) stream.
         `debug` (tests only) receives the device symbol / index planes [n_slices, B, 32*h*w] and z symbols."""
         mask_pol = self.mask_policy if mask_pol is None else mask_pol
@@ -715,6 +715,8 @@ class ChannelProgresssiveWACNN(nn.Module):
                                           cust_map=self._cust_map_act(E, cust_map, B, h, w), refine=refine)
         if debug is not None:
             debug.update(symbols=sym, indexes=idx, z_symbols=z_sym, y=E.to_nchw(y), y_hat_base=E.to_nchw(y_hat_base))
+        if _no_entropy:  # REM real_compress=False (CHProgREM.py:857-860): quantise only; y_hat is what a round trip gives
+            return {"strings": None, "shape": torch.Size([z.H, z.W]), "masks": masks, "y_hat": E.to_nchw(y_hat_out)}
         z_data, z_off = _ans.encode_batch(z_sym, z_idx, P["eb_tables"])
         y_data, y_off = _ans.encode_batch(sym.reshape(n_slices * B, n), idx.reshape(n_slices * B, n), P["gc_tables"])
         shape = torch.Size([z.H, z.W])

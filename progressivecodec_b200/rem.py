@@ -11,7 +11,8 @@ fused kernel (``pcodec_masked_residual``).
 
 ``checkpoint_rep`` (the refinement nets read a previously decoded check-level representation instead of the base
 slices, :773 / :989) and the ``escalation`` chain ``extract_chekpoint_representation_from_images`` (:336-372) are
-supported.  Out of scope (raise): training-time ``forward``/``forward_latent``, ``real_compress=False``.
+supported; ``real_compress=False`` quantises without running the entropy coder (``strings`` is None, ``y_hat`` is the
+latent a round trip would give).  Out of scope (raise): training-time ``forward``/``forward_latent``.
 """
 from __future__ import annotations
 
@@ -173,10 +174,9 @@ class PostRateProcessedNetwork(nn.Module):
     def compress(self, x, quality=0.0, mask_pol="point-based-std", checkpoint_rep=None, real_compress=True, used_qual=None,
                  debug: Optional[dict] = None):
         """CHProgREM.py:673-887 -> {"strings", "shape", "masks", "y_hat"}."""
-        if not real_compress:
-            raise NotImplementedError("real_compress=False (quantise without entropy coding) is a training-time path")
         self._prepare(self.base_net._device())  # pack the refinement nets on this thread, before any worker needs them
-        return self.base_net.compress(x, quality=quality, mask_pol=mask_pol, debug=debug, _rem=self, _rem_ckpt=checkpoint_rep)
+        return self.base_net.compress(x, quality=quality, mask_pol=mask_pol, debug=debug, _rem=self, _rem_ckpt=checkpoint_rep,
+                                      _no_entropy=not real_compress)
 
     @torch.no_grad()
     def decompress(self, strings, shape, quality, mask_pol=None, checkpoint_rep=None, timing=False, used_qual=None):

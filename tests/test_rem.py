@@ -102,6 +102,9 @@ def test_rem_gpu_vs_oracle_and_golden(name):
         # the decoder reproduces the encoder-side latent exactly (same kernels, same order)
         y_dec = torch.cat(dec["y_hat"], 1) if q == 0 else dec["y_hat"]
         assert torch.equal(y_dec, out["y_hat"]), q
+        if q in (0, 1):  # real_compress=False (CHProgREM.py:857-860): same latent, no entropy coder
+            nc = rem.compress(x.cuda(), quality=q, mask_pol="point-based-std", real_compress=False)
+            assert nc["strings"] is None and torch.equal(nc["y_hat"], out["y_hat"]), q
         if f"q{q}_mask_sum" in G.files and first is None:
             got = np.array([float(m.sum()) for m in out["masks"]])
             assert np.abs(got - G[f"q{q}_mask_sum"]).max() <= 2
