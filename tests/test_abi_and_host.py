@@ -244,3 +244,30 @@ def test_eval_helpers_dataset_padding_metrics(tmp_path):
     m.update(2.0)
     m.update(4.0, n=3)
     assert m.count == 4 and abs(m.avg - 3.5) < 1e-12
+
+
+def test_every_entry_point_validates_its_arguments_before_touching_the_device():
+    """Null pointers / zero sizes: PCODEC_ERR_BAD_ARG from every compute entry point (no CUDA call, so this runs without
+    a GPU); the device query fails loudly with a negative CUDA error when there is no device."""
+    import ctypes as C
+
+    from progressivecodec_b200 import _lib as L
+
+    lib = L.lib()
+    raw = lib._lib if hasattr(lib, "_lib") else lib
+    skip = {"pcodec_version", "pcodec_error_string", "pcodec_debug_tc_trace", "pcodec_launch_count",
+            "pcodec_reset_launch_count", "pcodec_conv_tc_release", "pcodec_device_info", "pcodec_selftest_rans_core_encode"}
+    checked = 0
+    for name, (res, args) in L.PROTOTYPES.items():
+        if name in skip:
+            continue
+        fn = getattr(raw, name)
+        fn.restype, fn.argtypes = res, args
+        zeros = [0.0 if a in (C.c_float, C.c_double) else (None if a is C.c_void_p or hasattr(a, "contents") else 0) for a in args]
+        assert fn(*zeros) == L.ERR_BAD_ARG, name
+        checked += 1
+    assert checked >= 20
+    if not torch.cuda.is_available():
+        fn = raw.pcodec_device_info
+        fn.restype, fn.argtypes = L.PROTOTYPES["pcodec_device_info"]
+        assert fn(None, None, None) < 0
