@@ -629,7 +629,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         const float4 z4_ = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 ra0 = NG == 2 ? load_res1(0) : z4_, ra1 = NG == 2 ? load_res1(1) : z4_;  // (NG == 1: no registers to spare)
         float acc[16];
-        if (NG == 1) {
+        if (NG != 2) {  // (96-register variants)
           tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective
           if (two) {
             float part[16];
@@ -666,7 +666,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
               make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
         __syncwarp();
         if (threadIdx.x == 0 && c0 == 0) TC_TRACE_G(6);
-        if (NG == 1) bias4 = load_bias(c0);
+        if (NG != 2) bias4 = load_bias(c0);
         const float4 rb0 = NG == 2 ? load_res1(2) : z4_, rb1 = NG == 2 ? load_res1(3) : z4_;
 #pragma unroll
         for (int i = 0; i < 4; i += 2) {  // two tile rows (i, i + 1) per call
@@ -1037,9 +1037,18 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   });
   if (attr_err != cudaSuccess) return -(int)attr_err;
   dim3 grid((unsigned)ceil_div64(P.M, TC_BM), (unsigned)h->n_tiles);
+  // PCODEC_TC_NG=3: a third converter group (18 warps).  EXPERIMENT, not yet run on hardware: with every load and TMEM
+  // store switched off the slab period is still ~760 clk, i.e. the two groups' wait -> LDS -> store -> arrive cycle is
+  // the floor of the long reductions (lesson 6).
+  static const bool three_groups = [] { const char *e = getenv("PCODEC_TC_NG"); return e && atoi(e) == 3; }();
   if (h->small)
     conv_taps_tc_kernel<1><<<grid, 32 * 10, smem, as_stream(stream)>>>(P, h->map_hi, h->map_lo);
-  else
+  else if (three_groups && smem >= 16 * 2048 + 2048) {
+    static const cudaError_t attr3 =
+        cudaFuncSetAttribute(conv_taps_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    if (attr3 != cudaSuccess) return -(int)attr3;
+    conv_taps_tc_kernel<3><<<grid, 32 * 18, smem, as_stream(stream)>>>(P, h->map_hi, h->map_lo);
+  } else
     conv_taps_tc_kernel<2><<<grid, 32 * 14, smem, as_stream(stream)>>>(P, h->map_hi, h->map_lo);
   PCODEC_RETURN_LAUNCH();
 }
