@@ -271,3 +271,42 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_device():
         fn = raw.pcodec_device_info
         fn.restype, fn.argtypes = L.PROTOTYPES["pcodec_device_info"]
         assert fn(None, None, None) < 0
+
+
+def test_branchfree_erf_polynomials_are_within_one_ulp():
+    """The GELU epilogue's branch-free erf (csrc/common.cuh): its coefficients, read from the source, evaluated with
+    fp32 FMA semantics on the host, stay within 1 ulp of double-precision erf over [-6, 6] and N(0, 2) samples."""
+    import re
+
+    import numpy as np
+    from scipy.special import erf
+
+    src = open(os.path.join(ROOT, "progressivecodec_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float erf_branchfree(float a)"):src.index("float gelu_erf(float x)")]
+    c = [np.float32(v) for v in re.findall(r"(-?\d\.\d+e-?\d+)f", body)]
+    assert len(c) == 13, c
+    thr = np.float32(re.search(r"t > (\d\.\d+)f", body).group(1))
+    f32 = np.float32
+
+    def fma(x, y, z):
+        return (np.float64(x) * np.float64(y) + np.float64(z)).astype(np.float32)
+
+    rng = np.random.default_rng(0)
+    a = np.concatenate([np.linspace(-6, 6, 400001), rng.standard_normal(200000) * 2]).astype(np.float32)
+    t, s = np.abs(a), (a * a).astype(np.float32)
+    r = fma(np.full_like(t, c[0]), t, c[1])
+    u = fma(np.full_like(t, c[2]), t, c[3])
+    r = fma(r, s, u)
+    for k in (4, 5, 6):
+        r = fma(r, t, c[k])
+    r = fma(r, t, -t)
+    big = np.copysign((f32(1) - np.exp(r.astype(np.float64)).astype(np.float32)).astype(np.float32), a)
+    q = np.full_like(t, c[7])
+    for k in range(8, 13):
+        q = fma(q, s, c[k])
+    small = fma(q, a, a)
+    got = np.where(t > thr, big, small).astype(np.float64)
+    ref = erf(a.astype(np.float64))
+    ulp = np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64)
+    ok = ulp > 0
+    assert float((np.abs(got - ref)[ok] / ulp[ok]).max()) <= 1.0
