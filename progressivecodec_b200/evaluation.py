@@ -125,9 +125,14 @@ class AverageMeter:
 @torch.no_grad()
 def compress_with_ac(model, filelist: Sequence[Union[str, Tensor]], device, epoch: int = -1,
                      pr_list: Sequence[float] = (0.05, 0.01), mask_pol: Optional[str] = None, writing: Optional[str] = None,
-                     cheating: bool = False, with_msssim: bool = True):
-    """training/step.py:277-404 (without the wandb logging, image dumps and gradient-derived custom maps).
-    `filelist` holds image paths or [3,H,W] tensors.  Returns ([bpp avg per level], [psnr avg], [decode seconds avg])."""
+                     cheating: bool = False, with_msssim: bool = True,
+                     custom_maps: Optional[Sequence[Optional[Tensor]]] = None, save_images: Optional[str] = None):
+    """training/step.py:277-404 (without the wandb logging).  `filelist` holds image paths or [3,H,W] tensors.
+    `custom_maps[i]` ([1, 32*n_prog, h/16, w/16] of the PADDED image, or None) replaces sigma in the masks of image i at
+    every level p > 0, as `customs_maps=True` does in the reference (:300-309, :326, :334) — the reference derives the
+    map from decoder gradients (`extract_dec_importance_map`), here the caller supplies it.  `save_images`: directory
+    for the reconstructions `<name><level index>.png` (:345-347).
+    Returns ([bpp avg per level], [psnr avg], [decode seconds avg])."""
     l = len(pr_list)
     bpp_loss = [AverageMeter() for _ in range(l)]
     psnr = [AverageMeter() for _ in range(l)]
@@ -139,14 +144,26 @@ def compress_with_ac(model, filelist: Sequence[Union[str, Tensor]], device, epoc
         h, w = x.size(2), x.size(3)
         pad, unpad = compute_padding(h, w, min_div=2 ** 6)  # pad to allow 6 strides of 2
         x_padded = F.pad(x, pad, mode="constant", value=0)
+        cmap = custom_maps[i] if custom_maps is not None else None
+        if cmap is not None:
+            cmap = cmap.to(device)
         for j, p in enumerate(pr_list):
-            data = model.compress(x_padded, quality=p, mask_pol=mask_pol)
-            torch.cuda.synchronize(device)
+            extra = {"cust_map": cmap} if (cmap is not None and p > 0) else {}
+            data = model.compress(x_padded, quality=p, mask_pol=mask_pol, **extra)
+            if torch.device(device).type == "cuda":
+                torch.cuda.synchronize(device)
             start = time.time()
-            out_dec = model.decompress(data["strings"], data["shape"], quality=p, mask_pol=mask_pol)
-            torch.cuda.synchronize(device)
+            out_dec = model.decompress(data["strings"], data["shape"], quality=p, mask_pol=mask_pol, **extra)
+            if torch.device(device).type == "cuda":
+                torch.cuda.synchronize(device)
             decoded_time = time.time() - start
             x_hat = F.pad(out_dec["x_hat"], unpad).clamp_(0.0, 1.0)
+            if save_images is not None:
+                from PIL import Image
+
+                os.makedirs(save_images, exist_ok=True)
+                img = (x_hat[0].permute(1, 2, 0).cpu() * 255.0).round().clamp_(0, 255).to(torch.uint8).numpy()
+                Image.fromarray(img).save(os.path.join(save_images, f"{name}{j}.png"))
             psnr_im = compute_psnr(x, x_hat)
             ms = compute_msssim(x, x_hat) if with_msssim and min(h, w) > 160 else float("nan")
             ms_db = -10 * math.log10(1 - ms) if ms == ms and ms < 1 else float("nan")

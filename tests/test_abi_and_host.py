@@ -310,3 +310,39 @@ def test_branchfree_erf_polynomials_are_within_one_ulp():
     ulp = np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64)
     ok = ulp > 0
     assert float((np.abs(got - ref)[ok] / ulp[ok]).max()) <= 1.0
+
+
+def test_compress_with_ac_routes_custom_maps_and_saves_images(tmp_path):
+    """Host logic of the evaluation harness with a stand-in codec: padding / unpadding, the custom map only at p > 0
+    (training/step.py:326,334), bpp accounting (:356-362), per-level files (:366-370, :397-403), image dumps (:345-347)."""
+    from progressivecodec_b200.evaluation import compress_with_ac
+
+    calls = []
+
+    class Fake:
+        def compress(self, x, quality, mask_pol=None, cust_map=None):
+            assert x.shape[2] % 64 == 0 and x.shape[3] % 64 == 0
+            calls.append(("c", quality, cust_map is not None))
+            self.x = x
+            nbytes = 10 + int(quality * 10)
+            return {"strings": [[[b"a" * nbytes]] * 2, [b"z" * 4]], "shape": (x.shape[2] // 64, x.shape[3] // 64)}
+
+        def decompress(self, strings, shape, quality, mask_pol=None, cust_map=None):
+            calls.append(("d", quality, cust_map is not None))
+            return {"x_hat": (self.x + 0.01 * (10 - quality)).clamp(0, 1)}
+
+    imgs = [torch.rand(3, 70, 100), torch.rand(3, 64, 64)]
+    maps = [torch.rand(1, 320, 8, 8), None]
+    bpp, ps, dt = compress_with_ac(Fake(), imgs, "cpu", pr_list=[0, 2, 5], writing=str(tmp_path), with_msssim=False,
+                                   custom_maps=maps, save_images=str(tmp_path / "img"))
+    assert [c for c in calls if c[0] == "c"] == [("c", 0, False), ("c", 2, True), ("c", 5, True),
+                                                 ("c", 0, False), ("c", 2, False), ("c", 5, False)]
+    assert [c[2] for c in calls if c[0] == "d"] == [False, True, True, False, False, False]
+    want0 = ((2 * 10 + 4) * 8 / (70 * 100) + (2 * 10 + 4) * 8 / (64 * 64)) / 2
+    assert abs(bpp[0] - want0) < 1e-12 and bpp[0] < bpp[1] < bpp[2] and ps[0] < ps[1] < ps[2]
+    assert sorted(os.listdir(tmp_path / "img")) == [f"image{i}{j}.png" for i in range(2) for j in range(3)]
+    from PIL import Image
+
+    assert Image.open(tmp_path / "img" / "image00.png").size == (100, 70)
+    lines = open(tmp_path / "level_1_.txt").read().strip().splitlines()
+    assert len(lines) == 3 and lines[0].startswith("SEQUENCE image0 BITS ") and lines[2].startswith("SEQUENCE AVG BITS ")
