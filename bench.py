@@ -93,15 +93,13 @@ class ClockSampler:
 # reference arm / cpu baseline (oracle port on the host cores)
 # ----------------------------------------------------------------------------------------------------------
 def _oracle_model():
-    import torch
-
+    """CPU oracle of the same synthetic-weights model, built WITHOUT the product package (oracle/synthetic_state.py:
+    skeleton fixture + name-keyed generator + the oracle's own update() restatement; pinned bit-identical to the
+    product's state_dict by tests/test_oracle_golden.py)."""
     from oracle.codec_port import CodecConfig, OracleCodec
-    from progressivecodec_b200 import ChannelProgresssiveWACNN, apply_synthetic_weights
+    from oracle.synthetic_state import synthetic_state_dict
 
-    net = ChannelProgresssiveWACNN(**AUTHORS).eval()
-    apply_synthetic_weights(net, seed=0)
-    net.update(force=True)
-    return net, OracleCodec(net.state_dict(), CodecConfig(**AUTHORS))
+    return OracleCodec(synthetic_state_dict("authors", seed=0), CodecConfig(**AUTHORS))
 
 
 def _cpu_time_sweep(orc, x, qualities):
@@ -115,14 +113,14 @@ def _cpu_time_sweep(orc, x, qualities):
 def run_reference(args):
     import torch
 
-    from oracle.gen_golden import synthetic_image
+    from oracle.synthetic_state import synthetic_image
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    _net, orc = _oracle_model()
+    orc = _oracle_model()
     x = synthetic_image((1, 3, H, W), seed=0)
     # one step = one image at one quality level (compress + decompress), cycling through the sweep
     qs = [QUALITIES[(3 * i) % len(QUALITIES)] for i in range(args.warmup + args.steps)]
@@ -202,8 +200,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from oracle.gen_golden import synthetic_image  # input generator only (not the checker)
     from progressivecodec_b200 import ChannelProgresssiveWACNN, _lib, apply_synthetic_weights
+    from progressivecodec_b200.synthetic import synthetic_image
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -236,34 +234,37 @@ def run_ours(args):
 
     h2d = [0]
     d2h = [0]
+    bytes_by_q = {}  # quality -> coded bytes of the batch (for the bpp of the synthetic workload)
+
+    def _upload(_q):  # one host->device copy of the batch per compress() call, from pinned host memory
+        h2d[0] += x_host.numel() * 4
+        return x_host.to(dev, non_blocking=True)
+
+    def _account(q, c, r):
+        nbytes = sum(len(s) for sl in c["strings"][0] for s in sl) + sum(len(s) for s in c["strings"][1])
+        bytes_by_q[q] = nbytes
+        d2h[0] += nbytes + r.numel() * 4  # strings out of compress(), x_hat back to the host
+        h2d[0] += nbytes                  # strings into decompress()
 
     def step_e2e():
+        """The sweep through the public API with HOST buffers: pinned image in (uploaded for every compress() call),
+        python `bytes` strings between the stages, x_hat copied back to pinned host memory."""
         h2d[0] = d2h[0] = 0
         if args.no_pipeline:
             for q in QUALITIES:
-                xd = x_host.to(dev, non_blocking=True)
-                h2d[0] += x_host.numel() * 4
-                c = net.compress(xd, quality=q)
-                nbytes = sum(len(s) for sl in c["strings"][0] for s in sl) + sum(len(s) for s in c["strings"][1])
-                d2h[0] += nbytes
+                c = net.compress(_upload(q), quality=q)
                 r = net.decompress(c["strings"], c["shape"], quality=q)["x_hat"]
                 xhat_host.copy_(r, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
-                h2d[0] += nbytes
-                d2h[0] += r.numel() * 4
+                _account(q, c, r)
             return
-        # host image in (pinned -> device), python `bytes` strings between the stages, x_hat copied back to the host
-        xd = x_host.to(dev, non_blocking=True)
-        h2d[0] += x_host.numel() * 4
 
         def on_result(q, c, r):
-            nbytes = sum(len(s) for sl in c["strings"][0] for s in sl) + sum(len(s) for s in c["strings"][1])
-            d2h[0] += nbytes + r["x_hat"].numel() * 4
-            h2d[0] += nbytes
             xhat_host.copy_(r["x_hat"], non_blocking=True)  # pinned destination
             torch.cuda.current_stream().synchronize()
+            _account(q, c, r["x_hat"])
 
-        pipeline.sweep(net, xd, QUALITIES, host_strings=True, on_result=on_result, keep=False)
+        pipeline.sweep(net, x_dev, QUALITIES, host_strings=True, on_result=on_result, keep=False, x_for_level=_upload)
 
     def barrier():
         if world > 1:
@@ -301,6 +302,7 @@ def run_ours(args):
     value = world * units * args.steps / t_dev
     e2e_value = world * units * e2e_steps / t_e2e
 
+    bpps = [8.0 * bytes_by_q[q] / (B * H * W) for q in QUALITIES]
     if rank == 0:
         peaks, kind = _peaks()
         roof = conv_roofline(net, peaks, kind)
@@ -311,7 +313,7 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            _n, orc = _oracle_model()
+            orc = _oracle_model()
             xs = x_host[:1].clone()
             sample_q = [0, 1.25, 10]
             _cpu_time_sweep(orc, xs, [5])
@@ -349,6 +351,11 @@ def run_ours(args):
                 "config": {"workload": f"compress+decompress, 13-level quality sweep (configs[1]), batch {B} x 768x512 per GPU",
                            "model": "ChannelProgresssiveWACNN authors' flags (mdmh-mem5-de), synthetic calibrated weights",
                            "batch_per_gpu": B, "qualities": QUALITIES,
+                           "bpp_synthetic": {"min": min(bpps), "max": max(bpps), "mean": sum(bpps) / len(bpps),
+                                             "note": "real rANS bytes of the e2e leg / pixels; the synthetic weights code "
+                                                     "several bpp (the reference's trained Kodak range is 0.19-0.69 bpp, "
+                                                     "result_list.py:168-213), so the entropy-coder share of the step is "
+                                                     "larger here than with a trained checkpoint"},
                            "l2": "256 MiB buffer written between steps; working set (0.6 GB weights + activations) >> 126 MB L2",
                            "pipeline": ("none" if args.no_pipeline else
                                         "compress(q+1) overlaps decompress(q): 2 host threads / CUDA streams (pipeline.sweep)"),
@@ -362,6 +369,91 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def dataset_image(i: int, base):
+    """Image i of the synthetic data set: base image i % len(base), rolled horizontally by 8 * (i // len(base)) pixels
+    (distinct images without generating N x 4.7 MB of filtered noise on the host)."""
+    import torch
+
+    return torch.roll(base[i % base.shape[0]], shifts=8 * (i // base.shape[0]), dims=-1)
+
+
+def run_dataset(args):
+    """BASELINE configs[4] as written: `--dataset N` images sharded over the ranks (contiguous blocks,
+    progressivecodec_b200.sharding), every rank codes its block in batches through pipeline.sweep with host strings,
+    and rank 0 gathers (bytes, crc32) of every image x level on the host — the same listing for any world size."""
+    import zlib
+
+    import torch
+    import torch.distributed as dist
+
+    from progressivecodec_b200 import ChannelProgresssiveWACNN, apply_synthetic_weights, pipeline
+    from progressivecodec_b200.sharding import shard_bounds
+    from progressivecodec_b200.synthetic import synthetic_image
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    net = ChannelProgresssiveWACNN(**AUTHORS).eval()
+    apply_synthetic_weights(net, seed=0)
+    net.update(force=True)
+    net = net.to(dev)
+    B, N = args.batch, args.dataset
+    base = torch.cat([synthetic_image((1, 3, H, W), seed=i) for i in range(64)])
+    lo, hi = shard_bounds(N, rank, world)
+    batches = [(s, min(hi, s + B)) for s in range(lo, hi, B)]
+    host = [torch.stack([dataset_image(i, base) for i in range(a, b)]).pin_memory() for a, b in batches]
+    pipeline.sweep(net, host[0].to(dev), QUALITIES, host_strings=True, keep=False)  # warm-up (tables, arenas)
+    sums = {}
+
+    def on_result_for(a):
+        def on_result(q, c, r):
+            ys, zs = c["strings"]
+            for j in range(len(zs)):
+                crc = zlib.crc32(zs[j])
+                n = len(zs[j])
+                for sl in ys:
+                    crc = zlib.crc32(sl[j], crc)
+                    n += len(sl[j])
+                sums[(a + j, q)] = (n, crc)
+        return on_result
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for (a, b), xh in zip(batches, host):
+        pipeline.sweep(net, xh.to(dev, non_blocking=True), QUALITIES, host_strings=True, keep=False,
+                       on_result=on_result_for(a))
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(sums, gathered, dst=0)  # the final host gather (no collective on the data path)
+        if rank == 0:
+            sums = {k: v for part in gathered for k, v in part.items()}
+    if rank == 0:
+        listing = sorted(sums.items())
+        digest = zlib.crc32(repr(listing).encode())
+        print(json.dumps({"metric": "768x512 img/s compress+decompress per quality", "value": N * len(QUALITIES) / t,
+                          "unit": "image-qualities/s", "n_gpus": world, "scaling": "strong", "seconds": t,
+                          "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"configs[4]: {N} synthetic 768x512 images sharded over {world} GPU(s), "
+                                                 f"compress+decompress at 13 levels, host strings, batch {B}"},
+                          "coded_bytes": sum(v[0] for _k, v in listing), "streams_digest_crc32": digest,
+                          "images_x_levels": len(listing)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -371,11 +463,31 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="compress/decompress strictly back to back")
+    ap.add_argument("--dataset", type=int, default=0,
+                    help="BASELINE configs[4]: N synthetic 768x512 images SHARDED over the ranks (strong scaling), "
+                         "compress+decompress at all 13 levels, per-image stream checksums gathered on rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return
+    try:
+        run_dataset(args) if args.dataset > 0 else run_ours(args)
+    except BaseException as e:  # noqa: BLE001
+        # A device fault leaves the CUDA context unusable: report WHAT failed (entry point + the library's flight
+        # recorder) and leave without running tensor destructors (they would abort with a bare SIGABRT).
+        import traceback
+
+        traceback.print_exc()
+        print(f"[bench] FAILED: {type(e).__name__}: {e}", file=sys.stderr)
+        try:
+            from progressivecodec_b200 import _lib
+
+            print("[bench] last launches (oldest first):\n" + _lib.recent_launches(), file=sys.stderr)
+        except Exception:  # noqa: BLE001
+            pass
+        sys.stderr.flush()
+        sys.stdout.flush()
+        os._exit(3)
 
 
 if __name__ == "__main__":

@@ -49,6 +49,15 @@ int pcodec_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* HOST. Number of kernels this library has launched since load / last reset (bench 'gpu_launches'). */
 int64_t pcodec_launch_count(void);
 void pcodec_reset_launch_count(void);
+/* HOST. Debug: when on (also PCODEC_SYNC_LAUNCHES=1 in the environment at load time) every entry point synchronises
+ * the device after its launches and names itself on stderr if the device faulted; the status is -cudaError_t.
+ * The reference has no counterpart (python exceptions only). */
+void pcodec_set_sync_launches(int on);
+/* HOST. Debug: writes the entry points of the last (up to 64) launches of this process, oldest first, one per line
+ * ("#seq thread <id> <entry point>") into buf; returns the number of characters written. */
+int pcodec_recent_launches(char *buf, int cap);
+/* HOST. Text for a status returned by any entry point (positive: PCODEC_ERR_*, negative: -cudaError_t). */
+const char *pcodec_error_string(int status);
 
 /* ------------------------------------------------------------------------------------------
  * Entropy coder

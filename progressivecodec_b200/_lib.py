@@ -57,6 +57,9 @@ PROTOTYPES = {
     "pcodec_device_info": (_i, [_vp, _vp, _vp]),
     "pcodec_launch_count": (_i64, []),
     "pcodec_reset_launch_count": (None, []),
+    "pcodec_set_sync_launches": (None, [_i]),
+    "pcodec_error_string": (C.c_char_p, [_i]),
+    "pcodec_recent_launches": (_i, [C.c_char_p, _i]),
     "pcodec_pmf_to_quantized_cdf": (_i, [_vp, _i, _i, _vp]),
     "pcodec_rans_encode_batch": (_i, [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _i, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "pcodec_rans_decode_batch": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
@@ -122,4 +125,12 @@ def check(rc: int, what: str = "") -> None:
         return
     if rc > 0:
         raise PcodecError(f"pcodec {what}: {_ERR.get(rc, 'error ' + str(rc))}")
-    raise PcodecError(f"pcodec {what}: CUDA error {-rc}")
+    raise PcodecError(f"pcodec {what}: CUDA error {-rc} ({lib().pcodec_error_string(rc).decode()})\n"
+                      f"last launches of this process (oldest first):\n{recent_launches()}")
+
+
+def recent_launches() -> str:
+    """Flight recorder of the library: entry points of the last launches (for attributing an asynchronous device fault)."""
+    buf = C.create_string_buffer(8192)
+    lib().pcodec_recent_launches(buf, len(buf))
+    return buf.value.decode(errors="replace")

@@ -154,6 +154,8 @@ def decode_segments(data: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor
 def pack_streams(strings: Sequence[bytes], device) -> Tuple[torch.Tensor, torch.Tensor]:
     """Host byte strings -> (uint8 CUDA blob with 8 bytes of zero slack, int64 CPU offsets)."""
     lens = [len(s) for s in strings]
+    if any(n % 4 for n in lens):  # the device decoder reads aligned 32-bit words (the coder only ever emits whole words)
+        raise L.PcodecError("rANS stream length is not a multiple of 4 bytes: not a stream of this coder / corrupted")
     offs = torch.zeros(len(strings) + 1, dtype=torch.int64)
     offs[1:] = torch.cumsum(torch.tensor(lens, dtype=torch.int64), 0)
     blob = torch.frombuffer(bytearray(b"".join(strings) + b"\0" * 8), dtype=torch.uint8)

@@ -90,6 +90,10 @@ class Header:
             raise L.PcodecError("container truncated inside the header")
         levels = list(struct.unpack_from(f"<{nl}f", blob, 20))
         lens = struct.unpack_from(f"<{1 + nb + nl * npg}I", blob, 20 + 4 * nl)
+        # untrusted input: the device decoder reads 32-bit words, so a stream whose length is not a multiple of 4
+        # would shift every later stream to a misaligned address (a sticky GPU fault, not a python exception)
+        if any(v % 4 or 0 < v < 8 for v in lens):
+            raise L.PcodecError("corrupt container: rANS stream lengths must be multiples of 4 and at least 8 bytes")
         layer = [list(lens[1 + nb + k * npg:1 + nb + (k + 1) * npg]) for k in range(nl)]
         return Header(levels, H, W, zh, zw, nb, npg, lens[0], list(lens[1:1 + nb]), layer)
 
@@ -116,7 +120,9 @@ def truncate(blob: bytes, n_layers: int) -> bytes:
 def encode_progressive(net, x: Tensor, levels: Sequence[float] = DEFAULT_LEVELS, mask_pol: Optional[str] = None) -> List[bytes]:
     """One encode of `x` [B,3,H,W] (H, W multiples of 64) -> one truncatable container per image."""
     _require(net)
-    levels = [float(v) for v in levels]
+    # the header stores the levels as f32 and the decoder recomputes the quantiles from what it reads there: round
+    # them to f32 HERE so that both sides derive bit-identical thresholds for any caller-supplied level
+    levels = [struct.unpack("<f", struct.pack("<f", float(v)))[0] for v in levels]
     if any(b <= a for a, b in zip(levels, levels[1:])) or not levels or levels[0] <= 0 or len(levels) > 15:
         raise ValueError("levels must be increasing, positive and at most 15")
     mask_pol = net.mask_policy if mask_pol is None else mask_pol

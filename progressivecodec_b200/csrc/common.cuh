@@ -9,15 +9,45 @@
 
 extern std::atomic<int64_t> g_pcodec_launches;
 
-#define PCODEC_COUNT_LAUNCH() g_pcodec_launches.fetch_add(1, std::memory_order_relaxed)
+// Flight recorder: the last launches of this process (entry point, stream), so that a device fault that surfaces at a
+// later synchronisation point can still be attributed (pcodec_recent_launches; printed by L.check on CUDA errors).
+void pcodec_note_launch(const char *what);
+#define PCODEC_COUNT_LAUNCH()                                        \
+  do {                                                               \
+    g_pcodec_launches.fetch_add(1, std::memory_order_relaxed);       \
+    pcodec_note_launch(__func__);                                    \
+  } while (0)
+
+// Debug knob (PCODEC_SYNC_LAUNCHES=1 or pcodec_set_sync_launches(1)): synchronise the device after every launch and
+// report WHICH entry point's kernel faulted (stderr + status), instead of a sticky error surfacing somewhere else later.
+extern std::atomic<int> g_pcodec_sync_launches;
+cudaError_t pcodec_sync_after_launch(const char *what);
 
 // After a kernel launch: translate launch errors into the C-ABI convention (-cudaError_t).
-#define PCODEC_RETURN_LAUNCH()                        \
-  do {                                                \
-    PCODEC_COUNT_LAUNCH();                            \
-    cudaError_t e__ = cudaGetLastError();             \
-    return e__ == cudaSuccess ? PCODEC_OK : -(int)e__; \
+#define PCODEC_RETURN_LAUNCH()                                                                           \
+  do {                                                                                                   \
+    PCODEC_COUNT_LAUNCH();                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                                                \
+    if (e__ == cudaSuccess && g_pcodec_sync_launches.load(std::memory_order_relaxed)) e__ = pcodec_sync_after_launch(__func__); \
+    return e__ == cudaSuccess ? PCODEC_OK : -(int)e__;                                                   \
   } while (0)
+
+// Same, for entry points that counted their (several) launches themselves.
+#define PCODEC_RETURN_STATUS()                                                                           \
+  do {                                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                                \
+    if (e__ == cudaSuccess && g_pcodec_sync_launches.load(std::memory_order_relaxed)) e__ = pcodec_sync_after_launch(__func__); \
+    return e__ == cudaSuccess ? PCODEC_OK : -(int)e__;                                                   \
+  } while (0)
+
+// One-time per-DEVICE opt-in (cudaFuncSetAttribute applies to the current device only): returns true when `mask` did not
+// yet have this device's bit, i.e. the caller must (re)apply the attribute; call pcodec_device_mark() once it succeeded.
+static inline bool pcodec_device_needs(std::atomic<uint64_t> &mask, uint64_t *bit_out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  *bit_out = 1ull << (dev & 63);
+  return !(mask.load(std::memory_order_acquire) & *bit_out);
+}
 
 #define PCODEC_CHECK_CUDA(expr)                      \
   do {                                               \

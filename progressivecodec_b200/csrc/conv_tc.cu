@@ -441,7 +441,8 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
       int seg = 0, tap = 0, st = 0;
       uint32_t eph = 1;  // parity to wait for on raw_empty
       for (int s = 0; s < n_steps;) {
-        const float *base = s_seg_ptr[seg] + chunk * 4;
+        const float *seg_base = s_seg_ptr[seg];
+        const float *base = seg_base + chunk * 4;
         const int ps = s_seg_ps[seg], seg_channels = s_seg_ch[seg];
         const int seg_slabs = (seg_channels + TC_BK - 1) / TC_BK;
         const int dy = s_dy[tap], dx = s_dx[tap];
@@ -461,8 +462,12 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
           const uint32_t mask = (kc * TC_BK + chunk * 4 < seg_channels) ? rowmask : 0u;
           if (!(P.debug & 1)) {
 #pragma unroll
-            for (int i = 0; i < RPT; ++i)
-              cp_async16(dst + soff[i], rowptr[i] + kc * TC_BK, ((mask >> i) & 1u) ? 16u : 0u);
+            for (int i = 0; i < RPT; ++i) {
+              // zero-fill copies (padding rows, channel chunks past the segment) never form an address outside the
+              // segment: a 0-byte LDGSTS must not depend on what the hardware does with an unmapped source address
+              const bool okc = (mask >> i) & 1u;
+              cp_async16(dst + soff[i], okc ? rowptr[i] + kc * TC_BK : seg_base, okc ? 16u : 0u);
+            }
           }
           cp_async_arrive_noinc(raw_full(st));  // per-thread: fires when this thread's copies have landed
           if (++st == stages) { st = 0; eph ^= 1u; }
@@ -930,7 +935,12 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
     }
   }
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return -(int)e;
+  if (e != cudaSuccess) {
+    cudaFree(h->dev_hi);
+    cudaFree(h->dev_lo);
+    delete h;
+    return -(int)e;
+  }
   *handle_out = h;
   return PCODEC_OK;
 }
@@ -1028,14 +1038,15 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   if (getenv("PCODEC_TC_VERBOSE"))
     fprintf(stderr, "[conv_tc] M=%lld bn=%d n_tiles=%d n_steps=%d stages=%d n_hi=%d ring=%d split=%d smem=%d small=%d\n",
             (long long)P.M, h->bn, h->n_tiles, n_steps, stages, P.n_hi_acc, P.a_ring, P.split, smem, h->small);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_taps_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_taps_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-  });
-  if (attr_err != cudaSuccess) return -(int)attr_err;
+  {  // opt-in to > 48 KB of dynamic shared memory, once per device (the attribute is per device)
+    static std::atomic<uint64_t> attr_mask{0};
+    uint64_t bit;
+    if (pcodec_device_needs(attr_mask, &bit)) {
+      PCODEC_CHECK_CUDA(cudaFuncSetAttribute(conv_taps_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+      PCODEC_CHECK_CUDA(cudaFuncSetAttribute(conv_taps_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      attr_mask.fetch_or(bit, std::memory_order_release);
+    }
+  }
   dim3 grid((unsigned)ceil_div64(P.M, TC_BM), (unsigned)h->n_tiles);
   // PCODEC_TC_NG=3: a third converter group (18 warps).  EXPERIMENT, not yet run on hardware: with every load and TMEM
   // store switched off the slab period is still ~760 clk, i.e. the two groups' wait -> LDS -> store -> arrive cycle is

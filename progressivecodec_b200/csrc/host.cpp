@@ -1,6 +1,9 @@
 // Host-side pieces of the C-ABI: version / device info / launch counter and pmf_to_quantized_cdf.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <vector>
@@ -22,6 +25,57 @@ extern "C" int pcodec_device_info(int *sm_count, int *cc_major, int *cc_minor) {
   if (cc_major) *cc_major = p.major;
   if (cc_minor) *cc_minor = p.minor;
   return PCODEC_OK;
+}
+
+std::atomic<int> g_pcodec_sync_launches{[] {
+  const char *e = getenv("PCODEC_SYNC_LAUNCHES");
+  return e && atoi(e) != 0 ? 1 : 0;
+}()};
+
+cudaError_t pcodec_sync_after_launch(const char *what) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) fprintf(stderr, "[pcodec] device fault after %s: %s (%d)\n", what, cudaGetErrorString(e), (int)e);
+  return e;
+}
+
+namespace {
+constexpr int kRing = 64;
+struct Note { const char *what; unsigned long long seq; unsigned long tid; };
+Note g_ring[kRing];
+std::atomic<unsigned long long> g_ring_seq{0};
+}  // namespace
+
+void pcodec_note_launch(const char *what) {
+  const unsigned long long seq = g_ring_seq.fetch_add(1, std::memory_order_relaxed);
+  Note &n = g_ring[seq % kRing];
+  n.what = what;
+  n.seq = seq;
+  n.tid = (unsigned long)pthread_self();
+}
+
+extern "C" int pcodec_recent_launches(char *buf, int cap) {
+  if (!buf || cap <= 0) return 0;
+  int pos = 0;
+  const unsigned long long end = g_ring_seq.load();
+  const unsigned long long begin = end > kRing ? end - kRing : 0;
+  for (unsigned long long q = begin; q < end && pos < cap - 96; ++q) {
+    const Note n = g_ring[q % kRing];
+    pos += snprintf(buf + pos, cap - pos, "#%llu thread %lx %s\n", n.seq, n.tid, n.what ? n.what : "?");
+  }
+  buf[pos < cap ? pos : cap - 1] = 0;
+  return pos;
+}
+
+extern "C" void pcodec_set_sync_launches(int on) { g_pcodec_sync_launches.store(on ? 1 : 0); }
+
+extern "C" const char *pcodec_error_string(int status) {
+  switch (status) {
+    case PCODEC_OK: return "ok";
+    case PCODEC_ERR_BAD_ARG: return "bad argument";
+    case PCODEC_ERR_UNSUPPORTED: return "unsupported configuration";
+    case PCODEC_ERR_OVERFLOW: return "capacity overflow";
+    default: return status < 0 ? cudaGetErrorString((cudaError_t)(-status)) : "unknown status";
+  }
 }
 
 extern "C" int64_t pcodec_launch_count(void) { return g_pcodec_launches.load(); }

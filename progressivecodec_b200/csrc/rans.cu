@@ -408,8 +408,7 @@ extern "C" int pcodec_rans_encode_batch(const int32_t *symbols, const int32_t *i
   rans_compact_kernel<<<dim3(n_streams, 4), 256, 0, st>>>(scratch, scratch_words, n_words, out_offsets, n_streams,
                                                           out_bytes, out_cap);
   PCODEC_COUNT_LAUNCH();
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? PCODEC_OK : -(int)e;
+  PCODEC_RETURN_STATUS();
 }
 
 extern "C" int pcodec_rans_decode_batch(const uint8_t *in_bytes, const int64_t *in_offsets, int n_streams,
@@ -475,8 +474,7 @@ extern "C" int pcodec_rans_encode_segments(const int32_t *symbols, const int32_t
   rans_compact_kernel<<<dim3(n_streams, 4), 256, 0, st>>>(scratch, scratch_words, n_words, out_offsets, n_streams,
                                                           out_bytes, out_cap);
   PCODEC_COUNT_LAUNCH();
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? PCODEC_OK : -(int)e;
+  PCODEC_RETURN_STATUS();
 }
 
 extern "C" int pcodec_rans_decode_segments(const uint8_t *in_bytes, const int64_t *starts, const int64_t *ends,

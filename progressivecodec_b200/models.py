@@ -19,6 +19,7 @@ scope: those arguments raise instead of silently running somethi
 from __future__ import annotations
 
 import math
+import threading
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -136,7 +137,8 @@ class ChannelProgresssiveWACNN(nn.Module):
         self.synthesis_tf32_passes = 3
         self.batch_independent_slices = True  # decode base slices 5..9 (mutually independent) as one phase
         self.decode_groups = 0          # 0 = auto (B // 4 capped at 4): image groups decoded on separate CUDA streams
-        self._streams = None
+        self._streams = {}               # decode-group streams per worker (created under _streams_lock)
+        self._streams_lock = threading.Lock()
 
     # ------------------------------------------------------------------------------------------------------
     # state handling
@@ -753,24 +755,21 @@ class ChannelProgresssiveWACNN(nn.Module):
         y_off_dev = y_off.to(dev)
         z_off_dev = z_off.to(dev)
         groups = self.decode_groups if self.decode_groups else max(1, min(4, B // 4))
-        groups = max(1, min(groups, B))
+        groups = max(1, min(groups, B, 7))  # engine slots: worker w owns slots 8w+1 .. 8w+7
         if groups == 1:
             # slot 1, not 0: slot 0 belongs to the encoder-side entry points, which pipeline.sweep() runs concurrently
             out = self._decompress_group(P, y_data, y_off_dev, z_data, z_off_dev, B, 0, B, shape, quality, mask_pol,
                                          slot=1 + 8 * _worker, cust_map=cust_map, rem=_rem, rem_ckpt=_rem_ckpt)
             return {"x_hat": out[0], "y_hat": out[1]} if _rem is not None else {"x_hat": out}
-        import threading
-
         from .sharding import shard_bounds
 
         cur = torch.cuda.current_stream(dev)
-        if self._streams is None:
-            self._streams = {}
-        if len(self._streams.get(_worker, ())) < groups:
-            # high priority: a group's entropy-decode launch is a handful of CTAs on its critical path; it should get
-            # the next free SM ahead of the wide convolution grids of other groups / of a concurrent compress()
-            self._streams[_worker] = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(groups)]
-        streams = self._streams[_worker]
+        with self._streams_lock:  # several decode workers may get here at once (pipeline.sweep, small batches)
+            if len(self._streams.get(_worker, ())) < groups:
+                # high priority: a group's entropy-decode launch is a handful of CTAs on its critical path; it should
+                # get the next free SM ahead of the wide convolution grids of other groups / of a concurrent compress()
+                self._streams[_worker] = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(groups)]
+            streams = self._streams[_worker]
         outs: List[Optional[Tensor]] = [None] * groups
         errs: List[Optional[BaseException]] = [None] * groups
 

@@ -15,10 +15,13 @@ from typing import Callable, List, Optional, Sequence
 
 import torch
 
+_streams_lock = threading.Lock()
+
 
 def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[str] = None, host_strings: bool = False,
           on_result: Optional[Callable[[float, dict, dict], None]] = None, keep: bool = True,
-          decode_workers: Optional[int] = None) -> List[Optional[torch.Tensor]]:
+          decode_workers: Optional[int] = None,
+          x_for_level: Optional[Callable[[float], torch.Tensor]] = None) -> List[Optional[torch.Tensor]]:
     """compress + decompress `x` at every level of `qualities`; returns the reconstructions (``x_hat`` per level).
 
     host_strings=False keeps the rANS streams on the device between the two stages (compress(...,
@@ -26,13 +29,26 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
     on_result(q, compressed, decompressed) is called on a worker thread after each level (its stream is
     synchronised at that point).  decode_workers: decompress() calls of different levels are independent too, so small
     batches (whose 16-phase decode chain leaves the GPU almost idle) run several of them concurrently; default
-    max(1, min(4, 8 // batch))."""
+    max(1, min(4, 8 // batch)).  x_for_level(q), when given, is called on the encoder stream before each level and
+    returns that level's input (e.g. a fresh host->device upload); `x` then only fixes the device and batch size."""
     dev = x.device
     caller_stream = torch.cuda.current_stream(dev)
-    enc_stream = torch.cuda.Stream(device=dev)
     n_workers = decode_workers if decode_workers else max(1, min(4, 8 // max(1, x.shape[0])))
     n_workers = max(1, min(4, n_workers))  # decompress() reserves 8 engine slots per worker
-    dec_streams = [torch.cuda.Stream(device=dev) for _ in range(n_workers)]
+    # One encoder stream and one stream per decode worker, created once per (model, device) and reused by every sweep:
+    # torch hands out streams round-robin from a pool of 32, and every new stream gets its own caching-allocator pool,
+    # so per-sweep streams grew the footprint by ~1.5 GB per sweep until the pool wrapped around.
+    with _streams_lock:
+        cache = net.__dict__.setdefault("_pipeline_streams", {})
+        have = cache.get(dev)
+        if have is None or len(have[1]) < n_workers:
+            have = (have[0] if have else torch.cuda.Stream(device=dev),
+                    (list(have[1]) if have else []) +
+                    [torch.cuda.Stream(device=dev) for _ in range(n_workers - (len(have[1]) if have else 0))])
+            cache[dev] = have
+    enc_stream, dec_streams = have[0], have[1][:n_workers]
+    for st in dec_streams:  # work of an earlier sweep's caller (e.g. frees recorded on its stream) is ordered first
+        st.wait_stream(caller_stream)
     enc_stream.wait_stream(caller_stream)
     q_items: "queue.Queue" = queue.Queue(maxsize=n_workers + 1)
     outs: List[Optional[torch.Tensor]] = [None] * len(qualities)
@@ -69,7 +85,8 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
             for i, q in enumerate(qualities):
                 if err:
                     break
-                c = net.compress(x, quality=q, mask_pol=mask_pol, return_device_streams=not host_strings)
+                xq = x_for_level(q) if x_for_level is not None else x
+                c = net.compress(xq, quality=q, mask_pol=mask_pol, return_device_streams=not host_strings)
                 enc_stream.synchronize()  # compress() has already synchronised to learn the stream lengths
                 q_items.put((i, q, c))
     finally:

@@ -102,3 +102,13 @@ def synthetic_tensor(name: str, p: torch.Tensor, seed: int, gains=None, biases=N
 def apply_synthetic_weights(model: torch.nn.Module, seed: int = 0, gains=None, biases=None) -> None:
     for name, p in model.named_parameters():
         p.copy_(synthetic_tensor(name, p, seed, gains, biases).to(p.dtype))
+
+
+def synthetic_image(shape, seed: int) -> torch.Tensor:
+    """Seeded smooth noise in [0,1] of shape [B,3,H,W] (SURVEY.md §8d 'Synthetic inputs'): uniform noise under a 5x5
+    box filter with reflected borders.  Same generator as the golden fixtures' inputs (tests pin the equality), kept
+    here so that bench.py / tools never import the checker package for their inputs."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    noise = torch.rand(*shape, generator=g)
+    padded = torch.nn.functional.pad(noise, (2, 2, 2, 2), mode="reflect")
+    return torch.nn.functional.avg_pool2d(padded, kernel_size=5, stride=1).contiguous()

@@ -129,15 +129,20 @@ def test_container_header_round_trip_and_prefix_logic():
     from progressivecodec_b200.container import Header, truncate
 
     levels = [0.05, 1.0, 10.0]
-    hdr = Header(levels, 512, 768, 8, 12, 10, 10, 111, [10 + i for i in range(10)],
-                 [[4 * (k + 1) if i % 2 == 0 else 0 for i in range(10)] for k in range(3)])
+    hdr = Header(levels, 512, 768, 8, 12, 10, 10, 112, [12 + 4 * i for i in range(10)],
+                 [[8 * (k + 1) if i % 2 == 0 else 0 for i in range(10)] for k in range(3)])
     raw = hdr.pack()
     assert len(raw) == hdr.size
     payload_len = hdr.prefix_end(3) - hdr.size
     blob = raw + bytes(range(256)) * (payload_len // 256 + 1)
     blob = blob[:hdr.prefix_end(3)]
     h2 = Header.parse(blob)
-    assert (h2.H, h2.W, h2.zh, h2.zw, h2.n_base, h2.n_prog, h2.z_len) == (512, 768, 8, 12, 10, 10, 111)
+    assert (h2.H, h2.W, h2.zh, h2.zw, h2.n_base, h2.n_prog, h2.z_len) == (512, 768, 8, 12, 10, 10, 112)
+    # untrusted lengths: a stream that is not a whole number of 32-bit words (or shorter than the coder's two flush
+    # words) would misalign every later stream on the device -> rejected on the host
+    for bad in (111, 4):
+        with pytest.raises(PcodecError, match="stream lengths"):
+            Header.parse(Header(levels, 512, 768, 8, 12, 10, 10, bad, hdr.base_len, hdr.layer_len).pack() + b"\0" * 4096)
     assert h2.base_len == hdr.base_len and h2.layer_len == hdr.layer_len
     assert [round(v, 4) for v in h2.levels] == levels
     ends = [h2.prefix_end(k) for k in range(4)]
@@ -148,8 +153,6 @@ def test_container_header_round_trip_and_prefix_logic():
         if k < 3:
             assert h2.layers_in(ends[k + 1] - 1) == k  # an incomplete layer does not count
     assert h2.layers_in(ends[0] - 1) == -1
-    import pytest
-
     with pytest.raises(PcodecError):
         Header.parse(b"nope" + blob[4:])
     with pytest.raises(PcodecError):
@@ -256,7 +259,8 @@ def test_every_entry_point_validates_its_arguments_before_touching_the_device():
     lib = L.lib()
     raw = lib._lib if hasattr(lib, "_lib") else lib
     skip = {"pcodec_version", "pcodec_error_string", "pcodec_debug_tc_trace", "pcodec_launch_count",
-            "pcodec_reset_launch_count", "pcodec_conv_tc_release", "pcodec_device_info", "pcodec_selftest_rans_core_encode"}
+            "pcodec_reset_launch_count", "pcodec_conv_tc_release", "pcodec_device_info", "pcodec_selftest_rans_core_encode",
+            "pcodec_set_sync_launches", "pcodec_recent_launches"}
     checked = 0
     for name, (res, args) in L.PROTOTYPES.items():
         if name in skip:

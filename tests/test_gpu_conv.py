@@ -319,3 +319,32 @@ def test_tc_two_cta_variants_match_torch(mode, monkeypatch):
         assert pc.tc is not None
         got = E.conv_new(pc, [_nhwc(x)], L_EPI_GELU)
         _close(_nchw(got), F.gelu(m(x)).detach())
+
+
+def test_tc_conv_large_m_tail_tile_and_wide_grid():
+    """The bench launches have millions of rows; the shape tests above stop at a few thousand.  3x3 32->32 over
+    5 x 1300 x 1301 pixels: M = 8 456 500 rows = 66 067 tiles (grid.x > 65 535, 32-bit pixel arithmetic near its
+    range), last tile has 52 valid rows.  Reference: torch's fp32 convolution (TF32 off) on the same device."""
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import Act, pack_conv2d
+
+    E = _engine(2)
+    torch.manual_seed(3)
+    m = nn.Conv2d(32, 32, 3, 1, 1)
+    x = torch.randn(5, 32, 1300, 1301, device="cuda")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.gelu(m.cuda()(x)).detach()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    pc = pack_conv2d(m, E.device, "big").attach_tc(3)
+    assert pc.tc is not None
+    out = E.conv_new(pc, [Act(x.permute(0, 2, 3, 1).contiguous())], L.EPI_GELU)
+    got = out.t.permute(0, 3, 1, 2)
+    assert (5 * 1300 * 1301) % 128 == 52 and (5 * 1300 * 1301 + 127) // 128 > 65535
+    scale = ref.pow(2).mean().sqrt().item()
+    err = (got - ref).abs().max().item()
+    assert err <= 8 * RTOL * scale, (err, scale)
+    # the last image's last rows (the tail tile) explicitly
+    assert torch.allclose(got[4, :, -1, -60:], ref[4, :, -1, -60:], atol=8 * RTOL * scale)

@@ -358,3 +358,96 @@ def test_800_level_scale_table_option():
         # q = 5: ~5 % of the indexes sit one level off and the first flipped rounding tie cascades through the remaining
         # slices of this 64x128 random-weight image (PSNR ~11 dB): a looser bound than the 0.02 dB of the 64-level tests
         assert abs(psnr(rec.cpu(), x) - psnr(torch.from_numpy(G[f"q{q}_x_hat"]), x)) <= (0.02 if q == 0 else 0.15), q
+
+
+def test_soak_batch64_pipelined_sweeps_equal_sequential():
+    """The bench configuration itself: batch 64 x 768x512, encoder thread + decode worker + 4 decode-group threads on
+    their own streams (pipeline.sweep), three full 13-level sweeps back to back.  Every reconstruction of every sweep
+    must be bit-identical to the strictly sequential compress()/decompress() of the same batch (same kernels, K order
+    and batch-invariant tiles), and no launch may fault.  Also pins what the threads rely on: the per-slot arenas and
+    descriptor caches are reused across sweeps without aliasing."""
+    from progressivecodec_b200 import pipeline
+
+    net, _ = build_pair("authors", "cuda")
+    x = torch.cat([synthetic_image((1, 3, 512, 768), seed=100 + i) for i in range(64)]).cuda()
+    qs = [0, 0.05, 0.1, 0.25, 0.5, 0.6, 0.75, 1, 1.25, 2, 3, 5, 10]
+    old_groups = net.decode_groups
+    net.decode_groups = 1
+    try:
+        ref = []
+        for q in qs:
+            c = net.compress(x, quality=q)
+            ref.append(net.decompress(c["strings"], c["shape"], quality=q)["x_hat"])
+    finally:
+        net.decode_groups = old_groups
+    assert (net.decode_groups or max(1, min(4, 64 // 4))) == 4
+    for sweep_no in range(3):
+        got = pipeline.sweep(net, x, qs, host_strings=(sweep_no == 1))
+        torch.cuda.synchronize()
+        for i, q in enumerate(qs):
+            assert torch.equal(got[i], ref[i]), (sweep_no, q)
+        del got
+
+
+def _stage_disagreement(dbg, odbg, b_gpu=0):
+    """(z symbols equal, first differing slice or None, fraction of that slice's elements that differ) for image b_gpu
+    of the GPU batch against a one-image oracle run."""
+    z_gpu = dbg["z_symbols"][b_gpu].cpu().reshape(-1)
+    z_equal = torch.equal(z_gpu, odbg["z_sym"].reshape(-1))
+    sym, idx = dbg["symbols"][:, b_gpu].cpu(), dbg["indexes"][:, b_gpu].cpu()
+    for s in range(sym.shape[0]):
+        bad = (sym[s] != odbg["symbols"][s].reshape(-1)) | (idx[s] != odbg["indexes"][s].reshape(-1))
+        if bad.any():
+            return z_equal, s, float(bad.float().mean())
+    return z_equal, None, 0.0
+
+
+@pytest.mark.parametrize("q", [0, 0.5, 5, 10])
+def test_headline_shape_768x512_vs_oracle(q):
+    """BASELINE configs[1] at its own shape (one 768x512 image, authors' flags) against the CPU oracle's round trip:
+    z symbols exact; quantised-symbol disagreement at the first diverging slice <= 1e-4 (<= 4 of 49 152 elements — up
+    to there both sides saw identical inputs); coded bytes within 0.5 %; PSNR within 0.02 dB; and when no plane
+    diverges the streams are byte-identical and the oracle's decoder reproduces our reconstruction from OUR bytes."""
+    net, orc = build_pair("authors", "cuda")
+    x = synthetic_image((1, 3, 512, 768), seed=5)
+    dbg, odbg = {}, {}
+    out = net.compress(x.cuda(), quality=q, debug=dbg)
+    o = orc.compress(x, quality=q, debug=odbg)
+    z_equal, first, frac = _stage_disagreement(dbg, odbg)
+    assert z_equal, "z symbols differ"
+    assert frac <= 1e-4, (q, first, frac)
+    b_gpu, b_ref = _total_bytes(out["strings"]), _total_bytes(o["strings"])
+    assert abs(b_gpu - b_ref) <= 0.005 * b_ref, (q, b_gpu, b_ref)
+    rec = net.decompress(out["strings"], out["shape"], quality=q)["x_hat"].cpu()
+    rec_orc = orc.decompress(o["strings"], tuple(o["shape"]), quality=q)["x_hat"]
+    assert abs(psnr(rec, x) - psnr(rec_orc, x)) <= 0.02, (q, psnr(rec, x), psnr(rec_orc, x))
+    if first is None:
+        assert out["strings"][0] == o["strings"][0] and out["strings"][1] == o["strings"][1]
+        cross = orc.decompress(out["strings"], tuple(out["shape"]), quality=q)["x_hat"]
+        assert abs(psnr(cross, x) - psnr(rec, x)) <= 0.02
+
+
+def test_headline_shape_images_of_a_pipelined_batch64_vs_oracle():
+    """Two images of a batch-64 pipelined sweep (the bench configuration) against one-image oracle runs: same bars as
+    the single-image test, so the headline throughput is measured on results that match the reference."""
+    from progressivecodec_b200 import pipeline
+
+    net, orc = build_pair("authors", "cuda")
+    x = torch.cat([synthetic_image((1, 3, 512, 768), seed=200 + i) for i in range(64)])
+    qs = [0.5, 10]
+    seen = {}
+    recs = pipeline.sweep(net, x.cuda(), qs, host_strings=True,
+                          on_result=lambda q, c, r: seen.__setitem__(q, c["strings"]))
+    for qi, q in enumerate(qs):
+        dbg = {}
+        net.compress(x.cuda(), quality=q, debug=dbg)  # planes of the same batch (deterministic kernels)
+        for b in (3, 61):
+            odbg = {}
+            o = orc.compress(x[b:b + 1], quality=q, debug=odbg)
+            z_equal, first, frac = _stage_disagreement(dbg, odbg, b)
+            assert z_equal and frac <= 1e-4, (q, b, first, frac)
+            mine = [[sl[b]] for sl in seen[q][0]], [seen[q][1][b]]
+            b_gpu, b_ref = _total_bytes(mine), _total_bytes(o["strings"])
+            assert abs(b_gpu - b_ref) <= 0.005 * b_ref, (q, b, b_gpu, b_ref)
+            rec_orc = orc.decompress(o["strings"], tuple(o["shape"]), quality=q)["x_hat"]
+            assert abs(psnr(recs[qi][b:b + 1].cpu(), x[b:b + 1]) - psnr(rec_orc, x[b:b + 1])) <= 0.02, (q, b)

@@ -145,3 +145,20 @@ def test_800_level_scale_table_matches_reference():
         assert out["strings"][0] == ref[0] and out["strings"][1] == ref[1], q
         rec = orc.decompress(ref, tuple(G[f"q{q}_shape"]), quality=q, mask_pol="point-based-std")["x_hat"]
         assert torch.equal(rec, torch.from_numpy(G[f"q{q}_x_hat"])), q
+
+
+def test_oracle_side_synthetic_state_dict_equals_the_products():
+    """bench.py's reference arm / cpu_baseline build their model from oracle/synthetic_state.py (no product package, no
+    libpcodec_b200.so in the process).  It must be the SAME model the CUDA arm runs: every entry bit-identical to
+    the product's state_dict() after apply_synthetic_weights() + update(), in the same order."""
+    from conftest import build_pair
+    from oracle.synthetic_state import synthetic_image, synthetic_state_dict
+    from progressivecodec_b200.synthetic import synthetic_image as product_image
+
+    net, _ = build_pair("authors")
+    ref = net.state_dict()
+    sd = synthetic_state_dict("authors", seed=0)
+    assert list(sd.keys()) == list(ref.keys())
+    for k, v in ref.items():
+        assert sd[k].dtype == v.dtype and sd[k].shape == v.shape and torch.equal(sd[k], v.cpu()), k
+    assert torch.equal(synthetic_image((1, 3, 64, 128), 3), product_image((1, 3, 64, 128), 3))
