@@ -226,6 +226,7 @@ int pcodec_bottleneck_likelihood(const float *z_hat, int z_ps, const float *para
 #define PCODEC_FLAG_SQUARE_INPUT 1   /* A = x*x (GDN) */
 #define PCODEC_FLAG_PIXEL_SHUFFLE2 2 /* output channel co -> pixel (2h + (co>>1&1), 2w + (co&1)), channel co>>2; applied
                                         after the epilogue (subpel_conv3x3, layers.py:20-24) */
+#define PCODEC_FLAG_NO_F32_OUT 8     /* fp16 path: write only the output planes (out_hi/out_lo), not `out` */
 #define PCODEC_FLAG_SUBPIXEL_NCHW 4  /* the 4 sub-pixel phases of a stride-2 transposed convolution computed as ONE
                                         3x3-neighbourhood GEMM: conv channel co = (2*py + px) * C + c is stored to the
                                         NCHW image out[n][c][2h+py][2w+px], C = out_channels (cout >= 4*C, tcgen05 path
@@ -236,6 +237,14 @@ typedef struct {
   int channels;     /* channels taken from this segment (multiple of 4) */
   int pixel_stride; /* floats between consecutive pixels */
 } pcodec_segment;
+
+/* Split-fp16 planes of an NHWC activation (the operand format of the fp16 tensor-core path, pcodec_split_planes):
+ *   x ~= hi + lo * 2^-11,  hi = fp16(x),  lo = fp16((x - hi) * 2^11)      (22 significant bits, |x| < 65504)
+ * two fp16 tensors with the geometry of the fp32 one; `pixel_stride` counts fp16 elements (a multiple of 8). */
+typedef struct {
+  const uint16_t *hi, *lo; /* fp16 bit patterns; hi == NULL: this segment has no planes */
+  int pixel_stride;
+} pcodec_planes;
 
 typedef struct {
   /* input: virtual channel-concatenation of n_segments tensors sharing [batch, in_h, in_w] */
@@ -263,11 +272,34 @@ typedef struct {
    * number of TF32 products per MAC: 3 = split accumulation (fp32-class accuracy), 1 = plain TF32 */
   const void *tc_weights;
   int tc_split;
+  /* fp16 tensor-core path (impl 3): the segments' split-fp16 planes (same order / channel windows as seg[]), optional
+   * planes of the OUTPUT written by the epilogue (out_hi != NULL; with PCODEC_FLAG_NO_F32_OUT `out` is not written and
+   * may be NULL), and a caller-owned scratch of PCODEC_CONV_PLAN_BYTES that pcodec_conv_plan() fills once per
+   * descriptor (tiling + TMA tensor maps of the activation planes) and pcodec_conv_taps() reads at every launch. */
+  pcodec_planes seg16[PCODEC_MAX_SEGMENTS];
+  uint16_t *out_hi, *out_lo;
+  int out_plane_stride;
+  void *plan;
 } pcodec_conv_desc;
 
-/* HOST descriptor, DEVICE tensors.  impl: 0 = auto (tcgen05 when desc->tc_weights is set and the shape is supported,
- * else SIMT), 1 = fp32 SIMT, 2 = tcgen05 (PCODEC_ERR_UNSUPPORTED if it cannot run this descriptor). */
+#define PCODEC_CONV_PLAN_BYTES 2048
+
+/* HOST descriptor, DEVICE tensors.  impl: 0 = auto (the fp16-split tcgen05 kernel when desc->plan is set, else the
+ * 3xTF32 tcgen05 kernel when desc->tc_weights is set and the shape is supported, else SIMT), 1 = fp32 SIMT,
+ * 2 = 3xTF32 tcgen05, 3 = fp16-split tcgen05 (2, 3: PCODEC_ERR_UNSUPPORTED if they cannot run this descriptor). */
 int pcodec_conv_taps(const pcodec_conv_desc *desc, int impl, void *stream);
+
+/* HOST. Build the launch plan of the fp16-split tcgen05 kernel into desc->plan (PCODEC_CONV_PLAN_BYTES, caller-owned):
+ * every segment needs planes (seg16[i].hi/lo), desc->tc_weights a handle of pcodec_conv_tc_prepare.  Returns
+ * PCODEC_ERR_UNSUPPORTED (and leaves the plan invalid) for shapes the kernel does not take. */
+int pcodec_conv_plan(pcodec_conv_desc *desc);
+
+/* fp32 NHWC window -> split-fp16 planes (see pcodec_planes).  src: [n_pixels] pixels of src_ps floats, `channels`
+ * (multiple of 8) converted; hi/lo: planes with pixel stride dst_ps (fp16 elements, multiple of 8).
+ * square != 0: the planes hold (x * 2^-4)^2 (GDN's x*x operand, gdn.py:50-63, pre-scaled for the fp16 range;
+ * the GDN convolution's weights carry the 2^8). */
+int pcodec_split_planes(const float *src, int src_ps, int64_t n_pixels, int channels, uint16_t *hi, uint16_t *lo,
+                        int dst_ps, int square, void *stream);
 
 /* Prepare weights for the tcgen05 kernel: takes the SIMT layout [n_taps][cin_total][cout] (device), builds the
  * K-major TF32 hi/lo copies [cout][n_taps*cin_total] and their TMA tensor maps; *handle_out is an opaque HOST handle

@@ -19,11 +19,18 @@ OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_OVERFLOW = 0, 1, 2, 3
 MASK_ONES, MASK_ZEROS, MASK_THRESHOLD = 0, 1, 2
 
 EPI_LINEAR, EPI_GELU, EPI_ADD, EPI_ADD_GELU, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP, EPI_CLAMP01, EPI_LEAKY, EPI_LEAKY_ADD = range(11)
-FLAG_SQUARE_INPUT, FLAG_PIXEL_SHUFFLE2, FLAG_SUBPIXEL_NCHW = 1, 2, 4
+FLAG_SQUARE_INPUT, FLAG_PIXEL_SHUFFLE2, FLAG_SUBPIXEL_NCHW, FLAG_NO_F32_OUT = 1, 2, 4, 8
 
 
 class Segment(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("channels", C.c_int), ("pixel_stride", C.c_int)]
+
+
+class Planes(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("pixel_stride", C.c_int)]
+
+
+CONV_PLAN_BYTES = 2048
 
 
 class ConvDesc(C.Structure):
@@ -40,6 +47,8 @@ class ConvDesc(C.Structure):
         ("r1", C.c_void_p), ("r1_pixel_stride", C.c_int),
         ("r2", C.c_void_p), ("r2_pixel_stride", C.c_int),
         ("tc_weights", C.c_void_p), ("tc_split", C.c_int),
+        ("seg16", Planes * MAX_SEGMENTS), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_plane_stride", C.c_int),
+        ("plan", C.c_void_p),
     ]
 
 
@@ -81,6 +90,8 @@ PROTOTYPES = {
     "pcodec_bottleneck_indexes": (_i, [_i, _i64, _i, _vp, _vp]),
     "pcodec_bottleneck_likelihood": (_i, [_vp, _i, _vp, _i, _i64, _i, _vp, _vp]),
     "pcodec_conv_taps": (_i, [C.POINTER(ConvDesc), _i, _vp]),
+    "pcodec_conv_plan": (_i, [C.POINTER(ConvDesc)]),
+    "pcodec_split_planes": (_i, [_vp, _i, _i64, _i, _vp, _vp, _i, _i, _vp]),
     "pcodec_conv_tc_prepare": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_void_p), _vp]),
     "pcodec_conv_tc_release": (None, [_vp]),
     "pcodec_window_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -258,6 +258,8 @@ int launch_simt(const ConvParams &P, cudaStream_t st) {
 
 int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream);  // conv_tc.cu (tcgen05 path)
 bool pcodec_conv_taps_tc_supported(const pcodec_conv_desc *desc);
+int pcodec_conv_taps_tc16(const pcodec_conv_desc *desc, void *stream);  // conv_tc16.cu (fp16-split tcgen05 path)
+bool pcodec_conv_taps_tc16_ready(const pcodec_conv_desc *desc);
 
 static int validate(const pcodec_conv_desc *d) {
   if (!d || !d->out || !d->weight) return PCODEC_ERR_BAD_ARG;
@@ -288,6 +290,7 @@ static int validate(const pcodec_conv_desc *d) {
 extern "C" int pcodec_conv_taps(const pcodec_conv_desc *desc, int impl, void *stream) {
   int rc = validate(desc);
   if (rc != PCODEC_OK) return rc;
+  if (impl == 3 || (impl == 0 && pcodec_conv_taps_tc16_ready(desc))) return pcodec_conv_taps_tc16(desc, stream);
   if (impl == 2 || (impl == 0 && pcodec_conv_taps_tc_supported(desc))) {
     if (!pcodec_conv_taps_tc_supported(desc)) return PCODEC_ERR_UNSUPPORTED;
     return pcodec_conv_taps_tc(desc, stream);

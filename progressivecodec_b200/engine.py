@@ -20,13 +20,42 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _Root:
+    """Per-buffer state shared by all channel windows of an activation: the split-fp16 planes (pcodec_planes: two fp16
+    tensors with the buffer's geometry) and which channel ranges of them hold current data."""
+
+    __slots__ = ("hi", "lo", "valid", "keep")
+
+    def __init__(self):
+        self.hi = 0          # device pointers of channel 0 of the planes (0 = not allocated)
+        self.lo = 0
+        self.valid = []      # disjoint [c0, c1) ranges whose planes are up to date
+        self.keep = None     # owner of the plane memory when it is not arena memory
+
+    def covers(self, c0: int, c1: int) -> bool:
+        for a, b in self.valid:
+            if a <= c0 and c1 <= b:
+                return True
+        return False
+
+    def mark(self, c0: int, c1: int) -> None:
+        out = []
+        for a, b in self.valid:
+            if b < c0 or c1 < a:
+                out.append((a, b))
+            else:
+                c0, c1 = min(a, c0), max(b, c1)
+        out.append((c0, c1))
+        self.valid = out
+
+
 class Act:
     """View of `C` channels starting at `c0` of an NHWC fp32 buffer [B, H, W, ps].
 
     Backed either by a torch tensor (`t`) or by a raw range of an `Arena`; kernels only need `ptr`/`ps`, so
     arena-backed views never construct a torch tensor on the hot path (`t` is materialised lazily)."""
 
-    __slots__ = ("_t", "base", "B", "H", "W", "C", "c0", "ps", "_owner")
+    __slots__ = ("_t", "base", "B", "H", "W", "C", "c0", "ps", "_owner", "_root")
 
     def __init__(self, t: Optional[Tensor] = None, c0: int = 0, channels: Optional[int] = None, *, base: int = 0,
                  shape: Optional[Tuple[int, int, int, int]] = None, owner=None):
@@ -43,6 +72,7 @@ class Act:
             self._owner = owner
         self.c0 = c0
         self.C = self.ps - c0 if channels is None else channels
+        self._root = _Root()  # shared by every channel window (slice) of this buffer
         assert 0 <= c0 and c0 + self.C <= self.ps
 
     @property
@@ -57,7 +87,7 @@ class Act:
 
     def slice(self, c0: int, channels: int) -> "Act":
         a = Act.__new__(Act)
-        a._t, a.base, a._owner = self._t, self.base, self._owner
+        a._t, a.base, a._owner, a._root = self._t, self.base, self._owner, self._root
         a.B, a.H, a.W, a.ps = self.B, self.H, self.W, self.ps
         a.c0, a.C = self.c0 + c0, channels
         assert a.c0 + channels <= self.ps
@@ -309,25 +339,92 @@ class Engine:
     def act(self, B: int, H: int, W: int, channels: int) -> Act:
         """Arena-backed NHWC activation (valid until the next begin() on this thread)."""
         ar = self._state().arena
-        return Act(base=ar.alloc(4 * B * H * W * channels), shape=(B, H, W, channels), owner=ar)
+        n = B * H * W * channels
+        a = Act(base=ar.alloc(8 * n), shape=(B, H, W, channels), owner=ar)
+        a._root.hi, a._root.lo = a.base + 4 * n, a.base + 6 * n  # split-fp16 planes: same lifetime as the fp32 data
+        return a
+
+    # -- split-fp16 planes (operand format of the fp16 tcgen05 kernel) -----------------------------------------
+    def _alloc_planes(self, a: Act) -> None:
+        """Arena activations get their plane space with the buffer itself (Engine.act), so it lives exactly as long as the
+        fp32 data whatever scope first converts it; torch-backed activations get a torch buffer of their own."""
+        r = a._root
+        if r.hi == 0:
+            n = a.B * a.H * a.W * a.ps
+            r.keep = torch.empty(2 * n, dtype=torch.float16, device=self.device)
+            r.hi = r.keep.data_ptr()
+            r.lo = r.hi + 2 * n
+
+    def planes(self, a: Act):
+        """(hi pointer, lo pointer) of window `a` in its buffer's planes, converting from fp32 when the window is not
+        current (inputs that no convolution epilogue produced: im2col patches, attention output, dequantised latents)."""
+        r = a._root
+        c1 = a.c0 + a.C
+        if r.hi == 0 or not r.covers(a.c0, c1):
+            if (a.c0 | a.C | a.ps) & 7:
+                return None
+            self._alloc_planes(a)
+            L.check(self.lib.pcodec_split_planes(a.ptr, a.ps, a.B * a.H * a.W, a.C, r.hi + 2 * a.c0, r.lo + 2 * a.c0, a.ps, 0,
+                                                 self.stream()), "split_planes")
+            r.mark(a.c0, c1)
+        return r.hi + 2 * a.c0, r.lo + 2 * a.c0
+
+    def squared_planes(self, a: Act):
+        """Temporary planes holding (x * 2^-4)^2 of window `a` (GDN operand), as a stand-alone Act-like triple."""
+        if (a.C | a.ps) & 7:
+            return None
+        n = 2 * a.B * a.H * a.W * a.C
+        base = self._state().arena.alloc(2 * n)
+        L.check(self.lib.pcodec_split_planes(a.ptr, a.ps, a.B * a.H * a.W, a.C, base, base + n, a.C, 1, self.stream()),
+                "split_planes(square)")
+        return base, base + n, a.C
 
     # -- generic tap conv --------------------------------------------------------------------------------
     def conv(self, pc: PackedConv, segs: Sequence[Act], out: Act, epi: int = L.EPI_LINEAR, r1: Optional[Act] = None,
-             r2: Optional[Act] = None, flags: int = 0) -> Act:
+             r2: Optional[Act] = None, flags: int = 0, fmt: int = 3) -> Act:
+        """fmt: what the epilogue writes — 1 = fp32 NHWC only, 2 = split-fp16 planes only (the consumer is another
+        convolution), 3 = both."""
         tls = self._state()
-        key = (id(pc), pc.w.data_ptr(), pc.tc, pc.tc_split, out.ptr, out.ps, epi, flags, r1.ptr if r1 is not None else 0,
+        key = (id(pc), pc.w.data_ptr(), pc.tc, pc.tc_split, out.ptr, out.ps, epi, flags, fmt, r1.ptr if r1 is not None else 0,
                r2.ptr if r2 is not None else 0, segs[0].B, segs[0].H, segs[0].W) + tuple((s.ptr, s.C, s.ps) for s in segs)
-        d = tls.descs.get(key)
-        if d is None:
-            d = self._build_desc(pc, segs, out, epi, r1, r2, flags)
+        use16 = self.conv_impl in (0, 3) and pc.tc is not None
+        seg_planes = None
+        if use16:
+            if flags & L.FLAG_SQUARE_INPUT:
+                sq = self.squared_planes(segs[0])
+                seg_planes = [sq] if sq is not None else None
+            else:
+                seg_planes = []
+                for s_ in segs:
+                    p = self.planes(s_)
+                    if p is None:
+                        seg_planes = None
+                        break
+                    seg_planes.append((p[0], p[1], s_.ps))
+            if seg_planes is not None and not (flags & L.FLAG_SUBPIXEL_NCHW) and (fmt & 2):
+                if (out.c0 | out.ps) & 3:
+                    fmt = 1
+                else:
+                    self._alloc_planes(out)
+            key = key + (seg_planes[0][0] if seg_planes else 0, out._root.hi)
+        ent = tls.descs.get(key)
+        if ent is None:
+            ent = self._build_desc(pc, segs, out, epi, r1, r2, flags, seg_planes, fmt)
             if len(tls.descs) > 20000:
                 tls.descs.clear()
-            tls.descs[key] = d
-        L.check(self.lib.pcodec_conv_taps(d, self.conv_impl, tls.stream), pc.name)
+            tls.descs[key] = ent
+        d, _plan, has_plan = ent
+        if use16 and not has_plan and self.conv_impl == 3:
+            raise L.PcodecError(f"conv[{pc.name}]: the fp16 tensor-core kernel cannot take this launch")
+        L.check(self.lib.pcodec_conv_taps(d, self.conv_impl if (has_plan or self.conv_impl != 3) else 0, tls.stream), pc.name)
+        if has_plan and d.out_hi:
+            out._root.mark(out.c0, out.c0 + (pc.cout // 4 if flags & L.FLAG_PIXEL_SHUFFLE2 else pc.cout))
+        elif out._root.valid:  # fp32 rewritten without planes: whatever planes covered this window are stale now
+            out._root.valid = [v for v in out._root.valid if v[1] <= out.c0 or v[0] >= out.c0 + out.C]
         return out
 
     def _build_desc(self, pc: PackedConv, segs: Sequence[Act], out: Act, epi: int, r1: Optional[Act],
-                    r2: Optional[Act], flags: int):
+                    r2: Optional[Act], flags: int, seg_planes=None, fmt: int = 1):
         a0 = segs[0]
         d = L.ConvDesc()
         cin = 0
@@ -372,7 +469,27 @@ class Engine:
         if r2 is not None:
             d.r2, d.r2_pixel_stride = r2.ptr, r2.ps
         d.tc_weights, d.tc_split = pc.tc, pc.tc_split
-        return d
+        plan, has_plan = None, False
+        if seg_planes is not None:
+            for i, (hi, lo, ps) in enumerate(seg_planes):
+                d.seg16[i].hi, d.seg16[i].lo, d.seg16[i].pixel_stride = hi, lo, ps
+            if (fmt & 2) and out._root.hi:
+                d.out_hi, d.out_lo = out._root.hi + 2 * out.c0, out._root.lo + 2 * out.c0
+                d.out_plane_stride = out.ps
+                if not (fmt & 1):
+                    d.flags = flags | L.FLAG_NO_F32_OUT
+            plan = (C.c_ubyte * L.CONV_PLAN_BYTES)()
+            d.plan = C.cast(plan, C.c_void_p)
+            rc = self.lib.pcodec_conv_plan(d)
+            if rc == L.OK:
+                has_plan = True
+            elif rc == L.ERR_UNSUPPORTED:
+                d.plan = None
+                d.out_hi = d.out_lo = None
+                d.flags = flags
+            else:
+                L.check(rc, f"conv_plan[{pc.name}]")
+        return d, plan, has_plan
 
     def conv_new(self, pc: PackedConv, segs: Sequence[Act], epi: int = L.EPI_LINEAR, r1=None, r2=None) -> Act:
         a0 = segs[0]
@@ -395,9 +512,11 @@ class Engine:
         Cimg = pc.image_channels
         out = torch.empty((x.B, Cimg, 2 * x.H, 2 * x.W), dtype=torch.float32, device=self.device)
         tls = self._state()
-        key = ("img", id(pc), pc.tc, pc.tc_split, x.ptr, x.ps, x.B, x.H, x.W, epi)
-        d = tls.descs.get(key)
-        if d is None:
+        use16 = self.conv_impl in (0, 3) and pc.tc is not None
+        pl = self.planes(x) if use16 else None
+        key = ("img", id(pc), pc.tc, pc.tc_split, x.ptr, x.ps, x.B, x.H, x.W, epi, pl[0] if pl else 0)
+        ent = tls.descs.get(key)
+        if ent is None:
             d = L.ConvDesc()
             d.seg[0].ptr, d.seg[0].channels, d.seg[0].pixel_stride = x.ptr, x.C, x.ps
             d.n_segments = 1
@@ -414,9 +533,20 @@ class Engine:
             d.out_pixel_stride = Cimg
             d.epilogue, d.flags = epi, L.FLAG_SUBPIXEL_NCHW
             d.tc_weights, d.tc_split = pc.tc, pc.tc_split
-            tls.descs[key] = d
+            d.out = out.data_ptr()
+            plan, has_plan = None, False
+            if pl is not None:
+                d.seg16[0].hi, d.seg16[0].lo, d.seg16[0].pixel_stride = pl[0], pl[1], x.ps
+                plan = (C.c_ubyte * L.CONV_PLAN_BYTES)()
+                d.plan = C.cast(plan, C.c_void_p)
+                has_plan = self.lib.pcodec_conv_plan(d) == L.OK
+                if not has_plan:
+                    d.plan = None
+            ent = (d, plan, has_plan)
+            tls.descs[key] = ent
+        d = ent[0]
         d.out = out.data_ptr()
-        L.check(self.lib.pcodec_conv_taps(d, self.conv_impl, tls.stream), pc.name)
+        L.check(self.lib.pcodec_conv_taps(d, self.conv_impl if (ent[2] or self.conv_impl != 3) else 0, tls.stream), pc.name)
         return out
 
     def gdn_new(self, pc: PackedConv, x: Act, inverse: bool) -> Act:
