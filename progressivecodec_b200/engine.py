@@ -123,8 +123,9 @@ class Arena:
         if self.off + nbytes > self.buf.numel():
             # grow: keep the old buffer alive (kernels in flight / live views), start a fresh, larger one
             self.retired.append(self.buf)
-            self.buf = torch.empty(max(2 * self.buf.numel(), self.off + nbytes + (64 << 20)), dtype=torch.uint8,
-                                   device=self.device)
+            # (the new buffer starts empty: it has to hold what is allocated from here on, not what came before)
+            self.buf = torch.empty(max(min(2 * self.buf.numel(), self.buf.numel() + (6 << 30)), nbytes + (256 << 20)),
+                                   dtype=torch.uint8, device=self.device)
             self.off = 0
             self.generation += 1
         p = self.buf.data_ptr() + self.off
@@ -336,12 +337,18 @@ class Engine:
         """`with E.scope():` — activations allocated inside are temporaries, released on exit."""
         return _ArenaScope(self._state().arena)
 
-    def act(self, B: int, H: int, W: int, channels: int) -> Act:
-        """Arena-backed NHWC activation (valid until the next begin() on this thread)."""
+    def act(self, B: int, H: int, W: int, channels: int, fmt: int = 3) -> Act:
+        """Arena-backed NHWC activation (valid until the next begin() on this thread).  fmt: which representations get
+        memory — 1 = fp32 only (consumers are not convolutions: GDN's x, attention's qkv), 2 = split-fp16 planes only
+        (the only consumers are convolutions), 3 = both.  The plane space is reserved with the buffer so that it lives
+        exactly as long as the data, whatever scope first converts it."""
         ar = self._state().arena
         n = B * H * W * channels
-        a = Act(base=ar.alloc(8 * n), shape=(B, H, W, channels), owner=ar)
-        a._root.hi, a._root.lo = a.base + 4 * n, a.base + 6 * n  # split-fp16 planes: same lifetime as the fp32 data
+        p = ar.alloc((4 * n if fmt & 1 else 0) + (4 * n if fmt & 2 else 0))
+        a = Act(base=p if fmt & 1 else 0, shape=(B, H, W, channels), owner=ar)
+        if fmt & 2:
+            q = p + (4 * n if fmt & 1 else 0)
+            a._root.hi, a._root.lo = q, q + 2 * n
         return a
 
     # -- split-fp16 planes (operand format of the fp16 tcgen05 kernel) -----------------------------------------
@@ -357,17 +364,25 @@ class Engine:
 
     def planes(self, a: Act):
         """(hi pointer, lo pointer) of window `a` in its buffer's planes, converting from fp32 when the window is not
-        current (inputs that no convolution epilogue produced: im2col patches, attention output, dequantised latents)."""
+        current (inputs that no convolution epilogue produced: im2col patches, attention output, dequantised latents).
+        A buffer created without plane space (fmt = 1) gets a temporary conversion in the current arena scope."""
         r = a._root
         c1 = a.c0 + a.C
-        if r.hi == 0 or not r.covers(a.c0, c1):
-            if (a.c0 | a.C | a.ps) & 7:
-                return None
+        if r.hi and r.covers(a.c0, c1):
+            return r.hi + 2 * a.c0, r.lo + 2 * a.c0
+        if (a.c0 | a.C | a.ps) & 7 or a.base == 0:
+            return None
+        if r.hi == 0 and a._owner is not None:  # arena activation without plane space: uncached temporary
+            n = a.B * a.H * a.W * a.ps
+            q = self._state().arena.alloc(4 * n)
+            hi, lo = q, q + 2 * n
+        else:
             self._alloc_planes(a)
-            L.check(self.lib.pcodec_split_planes(a.ptr, a.ps, a.B * a.H * a.W, a.C, r.hi + 2 * a.c0, r.lo + 2 * a.c0, a.ps, 0,
-                                                 self.stream()), "split_planes")
+            hi, lo = r.hi, r.lo
             r.mark(a.c0, c1)
-        return r.hi + 2 * a.c0, r.lo + 2 * a.c0
+        L.check(self.lib.pcodec_split_planes(a.ptr, a.ps, a.B * a.H * a.W, a.C, hi + 2 * a.c0, lo + 2 * a.c0, a.ps, 0,
+                                             self.stream()), "split_planes")
+        return hi + 2 * a.c0, lo + 2 * a.c0
 
     def squared_planes(self, a: Act):
         """Temporary planes holding (x * 2^-4)^2 of window `a` (GDN operand), as a stand-alone Act-like triple."""
@@ -401,12 +416,17 @@ class Engine:
                         seg_planes = None
                         break
                     seg_planes.append((p[0], p[1], s_.ps))
-            if seg_planes is not None and not (flags & L.FLAG_SUBPIXEL_NCHW) and (fmt & 2):
-                if (out.c0 | out.ps) & 3:
-                    fmt = 1
-                else:
-                    self._alloc_planes(out)
-            key = key + (seg_planes[0][0] if seg_planes else 0, out._root.hi)
+            if seg_planes is not None and (fmt & 2) and ((out.c0 | out.ps) & 3 or out._root.hi == 0):
+                fmt = 1  # no plane space behind this output (or a window the 8-byte plane stores cannot address)
+            if out.base == 0:
+                if seg_planes is None or not (fmt & 2):
+                    raise L.PcodecError(f"conv[{pc.name}]: planes-only output, but the fp16 kernel cannot run this launch")
+                fmt = 2
+            key = key + (seg_planes[0][0] if seg_planes else 0, out._root.hi, fmt)
+        if not use16 or seg_planes is None:
+            fmt = 1
+            if out.base == 0 or any(s_.base == 0 for s_ in segs):
+                raise L.PcodecError(f"conv[{pc.name}]: planes-only activation reached a launch the fp16 kernel cannot take")
         ent = tls.descs.get(key)
         if ent is None:
             ent = self._build_desc(pc, segs, out, epi, r1, r2, flags, seg_planes, fmt)
@@ -484,6 +504,8 @@ class Engine:
             if rc == L.OK:
                 has_plan = True
             elif rc == L.ERR_UNSUPPORTED:
+                if out.base == 0 or any(s.base == 0 for s in segs):
+                    raise L.PcodecError(f"conv_plan[{pc.name}]: unsupported launch with planes-only activations")
                 d.plan = None
                 d.out_hi = d.out_lo = None
                 d.flags = flags
@@ -491,20 +513,28 @@ class Engine:
                 L.check(rc, f"conv_plan[{pc.name}]")
         return d, plan, has_plan
 
-    def conv_new(self, pc: PackedConv, segs: Sequence[Act], epi: int = L.EPI_LINEAR, r1=None, r2=None) -> Act:
+    def _out_fmt(self, pc: PackedConv, fmt: int) -> int:
+        """Planes-only / planes outputs exist only on the fp16 tensor-core path."""
+        return fmt if (self.conv_impl in (0, 3) and pc.tc is not None) else 1
+
+    def conv_new(self, pc: PackedConv, segs: Sequence[Act], epi: int = L.EPI_LINEAR, r1=None, r2=None, fmt: int = 3) -> Act:
         a0 = segs[0]
-        out = self.act(a0.B, a0.H // pc.in_step, a0.W // pc.in_step, pc.cout)
-        return self.conv(pc, segs, out, epi, r1, r2)
+        fmt = self._out_fmt(pc, fmt)
+        out = self.act(a0.B, a0.H // pc.in_step, a0.W // pc.in_step, pc.cout, fmt)
+        return self.conv(pc, segs, out, epi, r1, r2, fmt=fmt)
 
-    def conv_shuffle_new(self, pc: PackedConv, x: Act, epi: int) -> Act:
-        out = self.act(x.B, 2 * x.H, 2 * x.W, pc.cout // 4)
-        return self.conv(pc, [x], out, epi, flags=L.FLAG_PIXEL_SHUFFLE2)
+    def conv_shuffle_new(self, pc: PackedConv, x: Act, epi: int, fmt: int = 3) -> Act:
+        fmt = self._out_fmt(pc, fmt)
+        out = self.act(x.B, 2 * x.H, 2 * x.W, pc.cout // 4, fmt)
+        return self.conv(pc, [x], out, epi, flags=L.FLAG_PIXEL_SHUFFLE2, fmt=fmt)
 
-    def deconv_new(self, phases: List[PackedConv], x: Act, epi: int = L.EPI_LINEAR, out: Optional[Act] = None) -> Act:
+    def deconv_new(self, phases: List[PackedConv], x: Act, epi: int = L.EPI_LINEAR, out: Optional[Act] = None,
+                   fmt: int = 3) -> Act:
+        fmt = self._out_fmt(phases[0], fmt)
         if out is None:
-            out = self.act(x.B, 2 * x.H, 2 * x.W, phases[0].cout)
+            out = self.act(x.B, 2 * x.H, 2 * x.W, phases[0].cout, fmt)
         for ph in phases:
-            self.conv(ph, [x], out, epi)
+            self.conv(ph, [x], out, epi, fmt=fmt)
         return out
 
     def deconv_image(self, pc: PackedConv, x: Act, epi: int) -> Tensor:
@@ -549,9 +579,10 @@ class Engine:
         L.check(self.lib.pcodec_conv_taps(d, self.conv_impl if (ent[2] or self.conv_impl != 3) else 0, tls.stream), pc.name)
         return out
 
-    def gdn_new(self, pc: PackedConv, x: Act, inverse: bool) -> Act:
-        out = self.act(x.B, x.H, x.W, x.C)
-        return self.conv(pc, [x], out, L.EPI_IGDN if inverse else L.EPI_GDN, r1=x, flags=L.FLAG_SQUARE_INPUT)
+    def gdn_new(self, pc: PackedConv, x: Act, inverse: bool, fmt: int = 3) -> Act:
+        fmt = self._out_fmt(pc, fmt)
+        out = self.act(x.B, x.H, x.W, x.C, fmt)
+        return self.conv(pc, [x], out, L.EPI_IGDN if inverse else L.EPI_GDN, r1=x, flags=L.FLAG_SQUARE_INPUT, fmt=fmt)
 
     # -- attention -----------------------------------------------------------------------------------------
     def window_attention(self, qkv: Act, rel_bias: Tensor, heads: int, ws: int, shift: int) -> Act:

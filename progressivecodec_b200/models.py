@@ -280,8 +280,8 @@ class ChannelProgresssiveWACNN(nn.Module):
         """ResidualUnit (layers.py:39-59): 1x1 -> GELU -> 3x3 -> GELU -> 1x1 -> (+x) -> GELU."""
         out = out or E.act(x.B, x.H, x.W, x.C)
         with E.scope():
-            h = E.conv_new(pk[0], [x], L.EPI_GELU)
-            h = E.conv_new(pk[1], [h], L.EPI_GELU)
+            h = E.conv_new(pk[0], [x], L.EPI_GELU, fmt=2)  # (intermediates feed convolutions only: split planes)
+            h = E.conv_new(pk[1], [h], L.EPI_GELU, fmt=2)
             E.conv(pk[2], [h], out, L.EPI_ADD_GELU, r1=x)
         return out
 
@@ -294,7 +294,7 @@ class ChannelProgresssiveWACNN(nn.Module):
                 a = self._ru(E, r, a)
             b = E.act(x.B, x.H, x.W, x.C)
             with E.scope():
-                qkv = E.conv_new(pk["qkv"], [x])
+                qkv = E.conv_new(pk["qkv"], [x], fmt=1)  # read by the attention kernel (fp32)
                 att = E.window_attention(qkv, pk["rel"], pk["heads"], pk["ws"], pk["shift"])
                 E.conv(pk["proj"], [att], b, L.EPI_ADD, r1=x)
             for r in pk["b"]:
@@ -305,14 +305,15 @@ class ChannelProgresssiveWACNN(nn.Module):
     def _g_a_one(self, E: Engine, pk, x: Tensor, out: Act) -> Act:
         """CHProg_cnn.py:131-144."""
         with E.scope():
+            # fmt: a conv feeding a GDN is read as fp32 (x and x*x), a GDN feeding a conv is read as planes only
             h = E.im2col_first(x, 5, 2, 2, 80)
-            h = E.conv_new(pk["c0"], [h])
-            h = E.gdn_new(pk["g1"], h, False)
-            h = E.conv_new(pk["c2"], [h])
+            h = E.conv_new(pk["c0"], [h], fmt=1)
+            h = E.gdn_new(pk["g1"], h, False, fmt=2)
+            h = E.conv_new(pk["c2"], [h], fmt=1)
             h = E.gdn_new(pk["g3"], h, False)
             h = self._win(E, pk["w4"], h)
-            h = E.conv_new(pk["c5"], [h])
-            h = E.gdn_new(pk["g6"], h, False)
+            h = E.conv_new(pk["c5"], [h], fmt=1)
+            h = E.gdn_new(pk["g6"], h, False, fmt=2)
             h = E.conv_new(pk["c7"], [h])
             self._win(E, pk["w8"], h, out)
         return out
@@ -335,13 +336,13 @@ class ChannelProgresssiveWACNN(nn.Module):
         pk = P["g_s"][which if self.multiple_decoder else 0]
         with E.scope():
             h = self._win(E, pk["w0"], y_hat)
-            h = E.deconv_new(pk["d1"], h)
-            h = E.gdn_new(pk["g2"], h, True)
-            h = E.deconv_new(pk["d3"], h)
+            h = E.deconv_new(pk["d1"], h, fmt=1)
+            h = E.gdn_new(pk["g2"], h, True, fmt=2)
+            h = E.deconv_new(pk["d3"], h, fmt=1)
             h = E.gdn_new(pk["g4"], h, True)
             h = self._win(E, pk["w5"], h)
-            h = E.deconv_new(pk["d6"], h)
-            h = E.gdn_new(pk["g7"], h, True)
+            h = E.deconv_new(pk["d6"], h, fmt=1)
+            h = E.gdn_new(pk["g7"], h, True, fmt=2)
             epi = L.EPI_CLAMP01 if clamp else L.EPI_LINEAR
             if isinstance(pk["d8"], PackedConv):  # merged sub-pixel phases, written straight to the NCHW image
                 return E.deconv_image(pk["d8"], h, epi)
@@ -354,17 +355,17 @@ class ChannelProgresssiveWACNN(nn.Module):
         with E.scope():
             h = y
             for j, pc in enumerate(P["h_a"][:4]):
-                h = E.conv_new(pc, [h], L.EPI_GELU)
+                h = E.conv_new(pc, [h], L.EPI_GELU, fmt=2)
             E.conv(P["h_a"][4], [h], out)
         return out
 
     @staticmethod
     def _h_s(E: Engine, pk, z_hat: Act, out: Act) -> Act:
         with E.scope():
-            h = E.conv_new(pk[0], [z_hat], L.EPI_GELU)
-            h = E.conv_shuffle_new(pk[1], h, L.EPI_GELU)
-            h = E.conv_new(pk[2], [h], L.EPI_GELU)
-            h = E.conv_shuffle_new(pk[3], h, L.EPI_GELU)
+            h = E.conv_new(pk[0], [z_hat], L.EPI_GELU, fmt=2)
+            h = E.conv_shuffle_new(pk[1], h, L.EPI_GELU, fmt=2)
+            h = E.conv_new(pk[2], [h], L.EPI_GELU, fmt=2)
+            h = E.conv_shuffle_new(pk[3], h, L.EPI_GELU, fmt=2)
             E.conv(pk[4], [h], out)
         return out
 
@@ -390,9 +391,9 @@ class ChannelProgresssiveWACNN(nn.Module):
     @staticmethod
     def _stack(E: Engine, pk, segs: Sequence[Act], out: Act, epi=L.EPI_LINEAR, r1=None, r2=None) -> Act:
         with E.scope():
-            h = E.conv_new(pk[0], segs, L.EPI_GELU)
+            h = E.conv_new(pk[0], segs, L.EPI_GELU, fmt=2)
             for j in (1, 2, 3):
-                h = E.conv_new(pk[j], [h], L.EPI_GELU)
+                h = E.conv_new(pk[j], [h], L.EPI_GELU, fmt=2)
             E.conv(pk[4], [h], out, epi, r1, r2)
         return out
 
@@ -403,7 +404,7 @@ class ChannelProgresssiveWACNN(nn.Module):
         out: List[Act] = []
         for a in acts:
             p = out[-1] if out else None
-            if (p is not None and p.base == a.base and p.ps == a.ps and (p.B, p.H, p.W) == (a.B, a.H, a.W)
+            if (p is not None and p._root is a._root and p.ps == a.ps and (p.B, p.H, p.W) == (a.B, a.H, a.W)
                     and p.c0 + p.C == a.c0):
                 out[-1] = p.slice(0, p.C + a.C)  # same buffer, adjacent channel window
             else:

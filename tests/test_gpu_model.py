@@ -371,15 +371,10 @@ def test_soak_batch64_pipelined_sweeps_equal_sequential():
     net, _ = build_pair("authors", "cuda")
     x = torch.cat([synthetic_image((1, 3, 512, 768), seed=100 + i) for i in range(64)]).cuda()
     qs = [0, 0.05, 0.1, 0.25, 0.5, 0.6, 0.75, 1, 1.25, 2, 3, 5, 10]
-    old_groups = net.decode_groups
-    net.decode_groups = 1
-    try:
-        ref = []
-        for q in qs:
-            c = net.compress(x, quality=q)
-            ref.append(net.decompress(c["strings"], c["shape"], quality=q)["x_hat"])
-    finally:
-        net.decode_groups = old_groups
+    ref = []
+    for q in qs:
+        c = net.compress(x, quality=q)
+        ref.append(net.decompress(c["strings"], c["shape"], quality=q)["x_hat"])
     assert (net.decode_groups or max(1, min(4, 64 // 4))) == 4
     for sweep_no in range(3):
         got = pipeline.sweep(net, x, qs, host_strings=(sweep_no == 1))
