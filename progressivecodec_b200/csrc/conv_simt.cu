@@ -262,13 +262,17 @@ int pcodec_conv_taps_tc16(const pcodec_conv_desc *desc, void *stream);  // conv_
 bool pcodec_conv_taps_tc16_ready(const pcodec_conv_desc *desc);
 
 static int validate(const pcodec_conv_desc *d) {
-  if (!d || !d->out || !d->weight) return PCODEC_ERR_BAD_ARG;
+  if (!d || !d->weight) return PCODEC_ERR_BAD_ARG;
+  const bool planes_out = (d->flags & PCODEC_FLAG_NO_F32_OUT) && d->out_hi && d->out_lo;  // fp16 path: no fp32 output
+  if (!d->out && !planes_out) return PCODEC_ERR_BAD_ARG;
   if (d->n_segments < 1 || d->n_segments > PCODEC_MAX_SEGMENTS) return PCODEC_ERR_BAD_ARG;
   if (d->n_taps < 1 || d->n_taps > PCODEC_MAX_TAPS) return PCODEC_ERR_BAD_ARG;
   int cin = 0;
   for (int s = 0; s < d->n_segments; ++s) {
     const pcodec_segment &sg = d->seg[s];
-    if (!sg.ptr || sg.channels <= 0 || sg.channels % BK != 0 || sg.pixel_stride < sg.channels) return PCODEC_ERR_BAD_ARG;
+    const bool planes_only = !sg.ptr && d->seg16[s].hi && d->seg16[s].lo;  // fp16 path: the segment exists as planes only
+    if ((!sg.ptr && !planes_only) || sg.channels <= 0 || sg.channels % BK != 0 || sg.pixel_stride < sg.channels)
+      return PCODEC_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(sg.ptr) & 15) || (sg.pixel_stride & 3)) return PCODEC_ERR_BAD_ARG;
     cin += sg.channels;
   }
@@ -291,6 +295,10 @@ extern "C" int pcodec_conv_taps(const pcodec_conv_desc *desc, int impl, void *st
   int rc = validate(desc);
   if (rc != PCODEC_OK) return rc;
   if (impl == 3 || (impl == 0 && pcodec_conv_taps_tc16_ready(desc))) return pcodec_conv_taps_tc16(desc, stream);
+  // the fp32-input kernels below need every segment and the output as fp32
+  if (!desc->out || (desc->flags & PCODEC_FLAG_NO_F32_OUT)) return PCODEC_ERR_UNSUPPORTED;
+  for (int s = 0; s < desc->n_segments; ++s)
+    if (!desc->seg[s].ptr) return PCODEC_ERR_UNSUPPORTED;
   if (impl == 2 || (impl == 0 && pcodec_conv_taps_tc_supported(desc))) {
     if (!pcodec_conv_taps_tc_supported(desc)) return PCODEC_ERR_UNSUPPORTED;
     return pcodec_conv_taps_tc(desc, stream);

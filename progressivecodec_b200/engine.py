@@ -422,7 +422,7 @@ class Engine:
                 if seg_planes is None or not (fmt & 2):
                     raise L.PcodecError(f"conv[{pc.name}]: planes-only output, but the fp16 kernel cannot run this launch")
                 fmt = 2
-            key = key + (seg_planes[0][0] if seg_planes else 0, out._root.hi, fmt)
+            key = key + (tuple(p_[0] for p_ in seg_planes) if seg_planes else 0, out._root.hi, fmt)
         if not use16 or seg_planes is None:
             fmt = 1
             if out.base == 0 or any(s_.base == 0 for s_ in segs):
@@ -450,7 +450,7 @@ class Engine:
         cin = 0
         for i, s in enumerate(segs):
             assert (s.B, s.H, s.W) == (a0.B, a0.H, a0.W)
-            d.seg[i].ptr = s.ptr
+            d.seg[i].ptr = s.ptr if s.base else None  # planes-only activation: no fp32 data behind it
             d.seg[i].channels = s.C
             d.seg[i].pixel_stride = s.ps
             cin += s.C
@@ -481,7 +481,7 @@ class Engine:
             assert (out.H, out.W, out.C) == (oh, ow, pc.cout), (pc.name, (out.H, out.W, out.C), (oh, ow, pc.cout))
             d.out_h, d.out_w = oh, ow
         assert out.B == a0.B
-        d.out = out.ptr
+        d.out = out.ptr if out.base else None
         d.out_pixel_stride = out.ps
         d.epilogue, d.flags = epi, flags
         if r1 is not None:
