@@ -37,7 +37,7 @@ constexpr int A_BYTES = BM * 128;      // one plane of one A tile
 constexpr int NWARPS = 10;             // 0: TMA producer, 1: TMEM alloc + MMA issuer, 2..9: epilogue (two per lane quarter)
 constexpr int EPI_WARPS = 8;
 constexpr int SMEM_LIMIT = 225 * 1024;
-constexpr int SMEM_HALF = 111 * 1024;  // two resident CTAs (tiles of <= 256 TMEM columns)
+constexpr int SMEM_HALF = 113 * 1024;  // two resident CTAs (tiles of <= 256 TMEM columns): 2 x (113 KB + 1 KB reserved) <= 228 KB
 constexpr uint32_t PLAN_MAGIC = 0x31366370u;
 constexpr float LO_SCALE = 2048.0f, LO_INV = 1.0f / 2048.0f;
 
@@ -150,7 +150,10 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
   const int b_bytes = bn * 128;
   const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;  // A_hi | A_lo | B_hi | B_lo
 
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (what the 128-byte swizzle
+  // atoms need); an alignment pad would cost the 2-stage configuration of the two-CTA tiles its second CTA
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
   auto a_hi = [&](int s) { return smem_base + s * stage_bytes; };
   auto a_lo = [&](int s) { return smem_base + s * stage_bytes + A_BYTES; };
   auto b_hi = [&](int s) { return smem_base + s * stage_bytes + 2 * A_BYTES; };
@@ -161,7 +164,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
   auto empty = [&](int s) { return bar_base + 8u * (stages + s); };  // MMAs of the stage retired (tcgen05.commit)
   const uint32_t tmem_full = bar_base + 8u * (2 * stages);
   const uint32_t tmem_slot = tmem_full + 8u;
-  uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t *smem_gen = smem_raw;
 
   const int n_acc = P.n_hi + 1;  // hi accumulators (round-robin over K slabs) + the lo accumulator
   uint32_t tmem_cols = 32;
@@ -465,9 +468,21 @@ int max_mma_per_acc() {
 }
 
 // N tile: the fewest tiles (least A re-reading) such that enough hi accumulators fit the 512 TMEM columns next to the lo
-// accumulator for no hi accumulator to see more than max_mma_per_acc() MMAs.
+// accumulator for no hi accumulator to see more than max_mma_per_acc() MMAs.  Short reductions (<= 24 hi MMAs, i.e. the
+// 1x1 layers) spend most of a tile's life in its serial prologue / epilogue: they get tiles of <= 128 columns with ONE hi
+// accumulator (<= 256 TMEM columns) so that two CTAs share an SM and overlap each other.
 int pick_bn16(int cout, int n_mma_hi, int *n_hi_out) {
   if (cout % 16 != 0) return 0;
+  static const bool pair_short = [] { const char *e = getenv("PCODEC_TC16_PAIR"); return !e || atoi(e) != 0; }();
+  if (pair_short && n_mma_hi <= 24) {
+    for (int tiles = 1; tiles <= 64; ++tiles) {
+      int bn = (cout + tiles - 1) / tiles;
+      bn = (bn + 15) & ~15;
+      if (bn > 128) continue;
+      *n_hi_out = 1;
+      return bn;
+    }
+  }
   const int need = std::min(4, std::max(1, (n_mma_hi + max_mma_per_acc() - 1) / max_mma_per_acc()));
   for (int relax = need; relax >= 1; --relax) {
     for (int tiles = 1; tiles <= 64; ++tiles) {
@@ -610,7 +625,7 @@ extern "C" int pcodec_conv_plan(pcodec_conv_desc *desc) {
   if (pl->bn == 0) return PCODEC_ERR_UNSUPPORTED;
   pl->n_tiles = (desc->cout + pl->bn - 1) / pl->bn;
   const int stage_bytes = 2 * A_BYTES + 2 * pl->bn * 128;
-  auto need = [&](int st) { return std::max(st * stage_bytes, EPI_WARPS * 2048) + 1024 + 8 * (2 * st + 2) + 64; };
+  auto need = [&](int st) { return std::max(st * stage_bytes, EPI_WARPS * 2048) + 8 * (2 * st + 2) + 64; };
   int tmem_cols = 32;
   while (tmem_cols < (pl->n_hi + 1) * pl->bn) tmem_cols <<= 1;
   // tiles of <= 256 TMEM columns: keep the footprint small enough for TWO resident CTAs (one's prologue / epilogue

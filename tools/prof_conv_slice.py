@@ -8,6 +8,6 @@ dev = torch.device("cuda", 0)
 m = nn.Conv2d(512, 224, 3, 1, 1)
 pc = pack_conv2d(m, dev, "cc_l1").attach_tc(3)
 x = Act(torch.randn(32, 32, 48, 512, device=dev)); out = new_act(32, 32, 48, 224, dev)
-E = Engine(dev, 2)
+E = Engine(dev, int(os.environ.get("IMPL", "3")))
 for _ in range(3): E.conv(pc, [x], out, L.EPI_GELU)
 torch.cuda.synchronize(); print("ok")
