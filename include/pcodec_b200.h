@@ -227,6 +227,8 @@ int pcodec_bottleneck_likelihood(const float *z_hat, int z_ps, const float *para
 #define PCODEC_FLAG_PIXEL_SHUFFLE2 2 /* output channel co -> pixel (2h + (co>>1&1), 2w + (co&1)), channel co>>2; applied
                                         after the epilogue (subpel_conv3x3, layers.py:20-24) */
 #define PCODEC_FLAG_NO_F32_OUT 8     /* fp16 path: write only the output planes (out_hi/out_lo), not `out` */
+#define PCODEC_FLAG_SQUARE_OUT_PLANES 16 /* fp16 path: the output PLANES hold (v * 2^-4)^2 instead of v — the x*x operand
+                                        of the GDN that follows (gdn.py:50-63), so no separate squaring pass runs */
 #define PCODEC_FLAG_SUBPIXEL_NCHW 4  /* the 4 sub-pixel phases of a stride-2 transposed convolution computed as ONE
                                         3x3-neighbourhood GEMM: conv channel co = (2*py + px) * C + c is stored to the
                                         NCHW image out[n][c][2h+py][2w+px], C = out_channels (cout >= 4*C, tcgen05 path
@@ -280,6 +282,8 @@ typedef struct {
   uint16_t *out_hi, *out_lo;
   int out_plane_stride;
   void *plan;
+  /* fp16 path: residual operands given as split planes (used when r1 / r2 is NULL; value = hi + lo * 2^-11) */
+  pcodec_planes r1_16, r2_16;
 } pcodec_conv_desc;
 
 #define PCODEC_CONV_PLAN_BYTES 2048

@@ -19,7 +19,7 @@ OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_OVERFLOW = 0, 1, 2, 3
 MASK_ONES, MASK_ZEROS, MASK_THRESHOLD = 0, 1, 2
 
 EPI_LINEAR, EPI_GELU, EPI_ADD, EPI_ADD_GELU, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_LRP, EPI_CLAMP01, EPI_LEAKY, EPI_LEAKY_ADD = range(11)
-FLAG_SQUARE_INPUT, FLAG_PIXEL_SHUFFLE2, FLAG_SUBPIXEL_NCHW, FLAG_NO_F32_OUT = 1, 2, 4, 8
+FLAG_SQUARE_INPUT, FLAG_PIXEL_SHUFFLE2, FLAG_SUBPIXEL_NCHW, FLAG_NO_F32_OUT, FLAG_SQUARE_OUT_PLANES = 1, 2, 4, 8, 16
 
 
 class Segment(C.Structure):
@@ -48,7 +48,7 @@ class ConvDesc(C.Structure):
         ("r2", C.c_void_p), ("r2_pixel_stride", C.c_int),
         ("tc_weights", C.c_void_p), ("tc_split", C.c_int),
         ("seg16", Planes * MAX_SEGMENTS), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_plane_stride", C.c_int),
-        ("plan", C.c_void_p),
+        ("plan", C.c_void_p), ("r1_16", Planes), ("r2_16", Planes),
     ]
 
 

@@ -283,8 +283,8 @@ static int validate(const pcodec_conv_desc *d) {
   const int epi = d->epilogue;
   const bool needs_r1 = epi == PCODEC_EPI_ADD || epi == PCODEC_EPI_ADD_GELU || epi == PCODEC_EPI_GATE ||
                         epi == PCODEC_EPI_GDN || epi == PCODEC_EPI_IGDN || epi == PCODEC_EPI_LRP || epi == PCODEC_EPI_LEAKY_ADD;
-  if (needs_r1 && !d->r1) return PCODEC_ERR_BAD_ARG;
-  if (epi == PCODEC_EPI_GATE && !d->r2) return PCODEC_ERR_BAD_ARG;
+  if (needs_r1 && !d->r1 && !d->r1_16.hi) return PCODEC_ERR_BAD_ARG;
+  if (epi == PCODEC_EPI_GATE && !d->r2 && !d->r2_16.hi) return PCODEC_ERR_BAD_ARG;
   if ((d->flags & PCODEC_FLAG_PIXEL_SHUFFLE2) && needs_r1) return PCODEC_ERR_UNSUPPORTED;
   if ((d->flags & PCODEC_FLAG_SUBPIXEL_NCHW) && (needs_r1 || (d->flags & PCODEC_FLAG_PIXEL_SHUFFLE2) || d->out_step != 1))
     return PCODEC_ERR_UNSUPPORTED;
@@ -299,6 +299,7 @@ extern "C" int pcodec_conv_taps(const pcodec_conv_desc *desc, int impl, void *st
   if (!desc->out || (desc->flags & PCODEC_FLAG_NO_F32_OUT)) return PCODEC_ERR_UNSUPPORTED;
   for (int s = 0; s < desc->n_segments; ++s)
     if (!desc->seg[s].ptr) return PCODEC_ERR_UNSUPPORTED;
+  if ((!desc->r1 && desc->r1_16.hi) || (!desc->r2 && desc->r2_16.hi)) return PCODEC_ERR_UNSUPPORTED;
   if (impl == 2 || (impl == 0 && pcodec_conv_taps_tc_supported(desc))) {
     if (!pcodec_conv_taps_tc_supported(desc)) return PCODEC_ERR_UNSUPPORTED;
     return pcodec_conv_taps_tc(desc, stream);

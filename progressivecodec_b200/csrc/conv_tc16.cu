@@ -268,13 +268,35 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
     const bool want_f32 = !(d.flags & PCODEC_FLAG_NO_F32_OUT);
     const bool want_planes = d.out_hi != nullptr;
 
-    if ((d.r1 || d.r2) && !shuffle && row_ok) {
+    const bool r1p = !d.r1 && d.r1_16.hi, r2p = !d.r2 && d.r2_16.hi;  // residuals given as split planes
+    if ((d.r1 || d.r2 || r1p || r2p) && !shuffle && row_ok) {
       // residual values do not depend on the accumulators: pull them into L2 while the main loop runs
       for (int c = half * 32; c < bn && n0 + c < d.cout; c += 64) {
         if (d.r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r1 + opix * d.r1_pixel_stride + n0 + c));
         if (d.r2) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r2 + opix * d.r2_pixel_stride + n0 + c));
       }
+      for (int c = half * 64; c < bn && n0 + c < d.cout; c += 128) {
+        if (r1p) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r1_16.hi + opix * d.r1_16.pixel_stride + n0 + c));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r1_16.lo + opix * d.r1_16.pixel_stride + n0 + c));
+        }
+        if (r2p) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r2_16.hi + opix * d.r2_16.pixel_stride + n0 + c));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r2_16.lo + opix * d.r2_16.pixel_stride + n0 + c));
+        }
+      }
     }
+    // residual operand for 4 channels of one pixel: fp32 when given, else reconstructed from its planes
+    auto load_res = [&](const float *r, int rps, const pcodec_planes &pl, bool from_planes, int64_t pix, int co, bool ok) {
+      if (!ok) return make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r) return __ldg(reinterpret_cast<const float4 *>(r + pix * rps + co));
+      if (!from_planes) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint2 h = __ldg(reinterpret_cast<const uint2 *>(pl.hi + pix * pl.pixel_stride + co));
+      const uint2 l = __ldg(reinterpret_cast<const uint2 *>(pl.lo + pix * pl.pixel_stride + co));
+      return make_float4(__fmaf_rn(h_lo_f(l.x), LO_INV, h_lo_f(h.x)), __fmaf_rn(h_hi_f(l.x), LO_INV, h_hi_f(h.x)),
+                         __fmaf_rn(h_lo_f(l.y), LO_INV, h_lo_f(h.y)), __fmaf_rn(h_hi_f(l.y), LO_INV, h_hi_f(h.y)));
+    };
+    const bool square_planes = (d.flags & PCODEC_FLAG_SQUARE_OUT_PLANES) != 0;
     const float out_scale = __ldg(P.w_scale + 1) * ((d.flags & PCODEC_FLAG_SQUARE_INPUT) ? 256.0f : 1.0f);
 
     mbar_wait(tmem_full, 0);
@@ -368,10 +390,10 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
           v.a = *reinterpret_cast<const float4 *>(stg + r0 * 64 + (((uint32_t)cc ^ ((uint32_t)(r0 >> 1) & 3u)) << 4));
           v.b = *reinterpret_cast<const float4 *>(stg + r1_ * 64 + (((uint32_t)cc ^ ((uint32_t)(r1_ >> 1) & 3u)) << 4));
           const bool ok0 = (ok_t >> i) & 1u, ok1 = (ok_t >> (i + 1)) & 1u;
-          a1.a = (d.r1 && ok0) ? __ldg(reinterpret_cast<const float4 *>(d.r1 + opix_t[i] * d.r1_pixel_stride + co)) : z4;
-          a1.b = (d.r1 && ok1) ? __ldg(reinterpret_cast<const float4 *>(d.r1 + opix_t[i + 1] * d.r1_pixel_stride + co)) : z4;
-          a2.a = (d.r2 && ok0) ? __ldg(reinterpret_cast<const float4 *>(d.r2 + opix_t[i] * d.r2_pixel_stride + co)) : z4;
-          a2.b = (d.r2 && ok1) ? __ldg(reinterpret_cast<const float4 *>(d.r2 + opix_t[i + 1] * d.r2_pixel_stride + co)) : z4;
+          a1.a = load_res(d.r1, d.r1_pixel_stride, d.r1_16, r1p, opix_t[i], co, ok0);
+          a1.b = load_res(d.r1, d.r1_pixel_stride, d.r1_16, r1p, opix_t[i + 1], co, ok1);
+          a2.a = load_res(d.r2, d.r2_pixel_stride, d.r2_16, r2p, opix_t[i], co, ok0);
+          a2.b = load_res(d.r2, d.r2_pixel_stride, d.r2_16, r2p, opix_t[i + 1], co, ok1);
           v.a = make_float4(v.a.x + bias4.x, v.a.y + bias4.y, v.a.z + bias4.z, v.a.w + bias4.w);
           v.b = make_float4(v.b.x + bias4.x, v.b.y + bias4.y, v.b.z + bias4.z, v.b.w + bias4.w);
           const F8 o = tc_epilogue8(d.epilogue, v, a1, a2, has_r2);
@@ -381,15 +403,22 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
           }
           if (want_planes) {
             uint2 h, l;
+            F8 p = o;
+            if (square_planes) {  // the GDN that follows reads (x * 2^-4)^2
+              p.a.x *= 0.0625f; p.a.y *= 0.0625f; p.a.z *= 0.0625f; p.a.w *= 0.0625f;
+              p.b.x *= 0.0625f; p.b.y *= 0.0625f; p.b.z *= 0.0625f; p.b.w *= 0.0625f;
+              p.a.x *= p.a.x; p.a.y *= p.a.y; p.a.z *= p.a.z; p.a.w *= p.a.w;
+              p.b.x *= p.b.x; p.b.y *= p.b.y; p.b.z *= p.b.z; p.b.w *= p.b.w;
+            }
             if (ok0) {
-              split2(o.a.x, o.a.y, h.x, l.x);
-              split2(o.a.z, o.a.w, h.y, l.y);
+              split2(p.a.x, p.a.y, h.x, l.x);
+              split2(p.a.z, p.a.w, h.y, l.y);
               *reinterpret_cast<uint2 *>(d.out_hi + opix_t[i] * d.out_plane_stride + co) = h;
               *reinterpret_cast<uint2 *>(d.out_lo + opix_t[i] * d.out_plane_stride + co) = l;
             }
             if (ok1) {
-              split2(o.b.x, o.b.y, h.x, l.x);
-              split2(o.b.z, o.b.w, h.y, l.y);
+              split2(p.b.x, p.b.y, h.x, l.x);
+              split2(p.b.z, p.b.w, h.y, l.y);
               *reinterpret_cast<uint2 *>(d.out_hi + opix_t[i + 1] * d.out_plane_stride + co) = h;
               *reinterpret_cast<uint2 *>(d.out_lo + opix_t[i + 1] * d.out_plane_stride + co) = l;
             }
@@ -587,6 +616,13 @@ extern "C" int pcodec_conv_plan(pcodec_conv_desc *desc) {
   }
   if (desc->r1 && ((desc->r1_pixel_stride & 3) || (reinterpret_cast<uintptr_t>(desc->r1) & 15))) return PCODEC_ERR_UNSUPPORTED;
   if (desc->r2 && ((desc->r2_pixel_stride & 3) || (reinterpret_cast<uintptr_t>(desc->r2) & 15))) return PCODEC_ERR_UNSUPPORTED;
+  for (const pcodec_planes *rp : {&desc->r1_16, &desc->r2_16})
+    if (rp->hi && (!rp->lo || (rp->pixel_stride & 3) || (reinterpret_cast<uintptr_t>(rp->hi) & 7) ||
+                   (reinterpret_cast<uintptr_t>(rp->lo) & 7)))
+      return PCODEC_ERR_UNSUPPORTED;
+  if ((desc->r1_16.hi || desc->r2_16.hi || (desc->flags & PCODEC_FLAG_SQUARE_OUT_PLANES)) &&
+      (desc->flags & (PCODEC_FLAG_PIXEL_SHUFFLE2 | PCODEC_FLAG_SUBPIXEL_NCHW)))
+    return PCODEC_ERR_UNSUPPORTED;
   if (desc->in_step < 1 || desc->in_step > 2) return PCODEC_ERR_UNSUPPORTED;
 
   // tile shape: th x tw = 128 output-grid pixels, tw a power of two; least padded area, then the squarest

@@ -24,13 +24,14 @@ class _Root:
     """Per-buffer state shared by all channel windows of an activation: the split-fp16 planes (pcodec_planes: two fp16
     tensors with the buffer's geometry) and which channel ranges of them hold current data."""
 
-    __slots__ = ("hi", "lo", "valid", "keep")
+    __slots__ = ("hi", "lo", "valid", "keep", "sq")
 
     def __init__(self):
         self.hi = 0          # device pointers of channel 0 of the planes (0 = not allocated)
         self.lo = 0
         self.valid = []      # disjoint [c0, c1) ranges whose planes are up to date
         self.keep = None     # owner of the plane memory when it is not arena memory
+        self.sq = False      # the planes hold (x * 2^-4)^2 (written by the producing conv for the GDN that follows)
 
     def covers(self, c0: int, c1: int) -> bool:
         for a, b in self.valid:
@@ -396,17 +397,26 @@ class Engine:
 
     # -- generic tap conv --------------------------------------------------------------------------------
     def conv(self, pc: PackedConv, segs: Sequence[Act], out: Act, epi: int = L.EPI_LINEAR, r1: Optional[Act] = None,
-             r2: Optional[Act] = None, flags: int = 0, fmt: int = 3) -> Act:
+             r2: Optional[Act] = None, flags: int = 0, fmt: int = 3, square_planes: bool = False) -> Act:
         """fmt: what the epilogue writes — 1 = fp32 NHWC only, 2 = split-fp16 planes only (the consumer is another
-        convolution), 3 = both."""
+        convolution), 3 = both.  square_planes: the planes get (v * 2^-4)^2, the operand of the GDN that follows."""
         tls = self._state()
-        key = (id(pc), pc.w.data_ptr(), pc.tc, pc.tc_split, out.ptr, out.ps, epi, flags, fmt, r1.ptr if r1 is not None else 0,
-               r2.ptr if r2 is not None else 0, segs[0].B, segs[0].H, segs[0].W) + tuple((s.ptr, s.C, s.ps) for s in segs)
+        if square_planes and self.conv_impl in (0, 3) and pc.tc is not None and out._root.hi and not ((out.c0 | out.ps) & 3):
+            flags |= L.FLAG_SQUARE_OUT_PLANES
+            fmt = 3
+        key = (id(pc), pc.w.data_ptr(), pc.tc, pc.tc_split, out.ptr, out.ps, epi, flags, fmt,
+               (r1.ptr if r1.base else -(r1._root.hi + 2 * r1.c0)) if r1 is not None else 0,
+               (r2.ptr if r2.base else -(r2._root.hi + 2 * r2.c0)) if r2 is not None else 0,
+               segs[0].B, segs[0].H, segs[0].W) + tuple((s.ptr, s.C, s.ps) for s in segs)
         use16 = self.conv_impl in (0, 3) and pc.tc is not None
         seg_planes = None
         if use16:
             if flags & L.FLAG_SQUARE_INPUT:
-                sq = self.squared_planes(segs[0])
+                x0 = segs[0]
+                if x0._root.sq:  # the producing conv already wrote the squares
+                    sq = (x0._root.hi + 2 * x0.c0, x0._root.lo + 2 * x0.c0, x0.ps)
+                else:
+                    sq = self.squared_planes(x0)
                 seg_planes = [sq] if sq is not None else None
             else:
                 seg_planes = []
@@ -437,7 +447,9 @@ class Engine:
         if use16 and not has_plan and self.conv_impl == 3:
             raise L.PcodecError(f"conv[{pc.name}]: the fp16 tensor-core kernel cannot take this launch")
         L.check(self.lib.pcodec_conv_taps(d, self.conv_impl if (has_plan or self.conv_impl != 3) else 0, tls.stream), pc.name)
-        if has_plan and d.out_hi:
+        if has_plan and d.out_hi and (flags & L.FLAG_SQUARE_OUT_PLANES):
+            out._root.sq = True
+        elif has_plan and d.out_hi:
             out._root.mark(out.c0, out.c0 + (pc.cout // 4 if flags & L.FLAG_PIXEL_SHUFFLE2 else pc.cout))
         elif out._root.valid:  # fp32 rewritten without planes: whatever planes covered this window are stale now
             out._root.valid = [v for v in out._root.valid if v[1] <= out.c0 or v[0] >= out.c0 + out.C]
@@ -484,10 +496,17 @@ class Engine:
         d.out = out.ptr if out.base else None
         d.out_pixel_stride = out.ps
         d.epilogue, d.flags = epi, flags
-        if r1 is not None:
-            d.r1, d.r1_pixel_stride = r1.ptr, r1.ps
-        if r2 is not None:
-            d.r2, d.r2_pixel_stride = r2.ptr, r2.ps
+        for r, name in ((r1, "r1"), (r2, "r2")):
+            if r is None:
+                continue
+            if r.base:
+                setattr(d, name, r.ptr)
+                setattr(d, name + "_pixel_stride", r.ps)
+            else:  # planes-only residual: the epilogue reconstructs hi + lo * 2^-11
+                if not r._root.covers(r.c0, r.c0 + r.C) or r._root.sq:
+                    raise L.PcodecError(f"conv[{pc.name}]: residual operand has neither fp32 data nor current planes")
+                pl = getattr(d, name + "_16")
+                pl.hi, pl.lo, pl.pixel_stride = r._root.hi + 2 * r.c0, r._root.lo + 2 * r.c0, r.ps
         d.tc_weights, d.tc_split = pc.tc, pc.tc_split
         plan, has_plan = None, False
         if seg_planes is not None:
@@ -517,11 +536,12 @@ class Engine:
         """Planes-only / planes outputs exist only on the fp16 tensor-core path."""
         return fmt if (self.conv_impl in (0, 3) and pc.tc is not None) else 1
 
-    def conv_new(self, pc: PackedConv, segs: Sequence[Act], epi: int = L.EPI_LINEAR, r1=None, r2=None, fmt: int = 3) -> Act:
+    def conv_new(self, pc: PackedConv, segs: Sequence[Act], epi: int = L.EPI_LINEAR, r1=None, r2=None, fmt: int = 3,
+                 square_planes: bool = False) -> Act:
         a0 = segs[0]
-        fmt = self._out_fmt(pc, fmt)
+        fmt = self._out_fmt(pc, 3 if square_planes else fmt)
         out = self.act(a0.B, a0.H // pc.in_step, a0.W // pc.in_step, pc.cout, fmt)
-        return self.conv(pc, segs, out, epi, r1, r2, fmt=fmt)
+        return self.conv(pc, segs, out, epi, r1, r2, fmt=fmt, square_planes=square_planes)
 
     def conv_shuffle_new(self, pc: PackedConv, x: Act, epi: int, fmt: int = 3) -> Act:
         fmt = self._out_fmt(pc, fmt)
@@ -529,12 +549,12 @@ class Engine:
         return self.conv(pc, [x], out, epi, flags=L.FLAG_PIXEL_SHUFFLE2, fmt=fmt)
 
     def deconv_new(self, phases: List[PackedConv], x: Act, epi: int = L.EPI_LINEAR, out: Optional[Act] = None,
-                   fmt: int = 3) -> Act:
-        fmt = self._out_fmt(phases[0], fmt)
+                   fmt: int = 3, square_planes: bool = False) -> Act:
+        fmt = self._out_fmt(phases[0], 3 if square_planes else fmt)
         if out is None:
             out = self.act(x.B, 2 * x.H, 2 * x.W, phases[0].cout, fmt)
         for ph in phases:
-            self.conv(ph, [x], out, epi, fmt=fmt)
+            self.conv(ph, [x], out, epi, fmt=fmt, square_planes=square_planes)
         return out
 
     def deconv_image(self, pc: PackedConv, x: Act, epi: int) -> Tensor:

@@ -276,43 +276,48 @@ class ChannelProgresssiveWACNN(nn.Module):
     # network pieces on the engine
     # ------------------------------------------------------------------------------------------------------
     @staticmethod
-    def _ru(E: Engine, pk, x: Act, out: Optional[Act] = None) -> Act:
+    def _ru(E: Engine, pk, x: Act, out: Optional[Act] = None, fmt: int = 3) -> Act:
         """ResidualUnit (layers.py:39-59): 1x1 -> GELU -> 3x3 -> GELU -> 1x1 -> (+x) -> GELU."""
-        out = out or E.act(x.B, x.H, x.W, x.C)
+        fmt = E._out_fmt(pk[2], fmt)
+        out = out or E.act(x.B, x.H, x.W, x.C, fmt)
         with E.scope():
             h = E.conv_new(pk[0], [x], L.EPI_GELU, fmt=2)  # (intermediates feed convolutions only: split planes)
             h = E.conv_new(pk[1], [h], L.EPI_GELU, fmt=2)
-            E.conv(pk[2], [h], out, L.EPI_ADD_GELU, r1=x)
+            E.conv(pk[2], [h], out, L.EPI_ADD_GELU, r1=x, fmt=fmt if out.base == 0 else 3)
         return out
 
     def _win(self, E: Engine, pk, x: Act, out: Optional[Act] = None) -> Act:
         """Win_noShift_Attention (layers.py:69-75)."""
         out = out or E.act(x.B, x.H, x.W, x.C)
         with E.scope():
+            # the units' outputs feed convolutions and residual adds only: split planes (the epilogues read the
+            # residual operand from the planes as hi + lo * 2^-11)
             a = x
             for r in pk["a"]:
-                a = self._ru(E, r, a)
-            b = E.act(x.B, x.H, x.W, x.C)
+                a = self._ru(E, r, a, fmt=2)
+            fb = E._out_fmt(pk["proj"], 2)
+            b = E.act(x.B, x.H, x.W, x.C, fb)
             with E.scope():
                 qkv = E.conv_new(pk["qkv"], [x], fmt=1)  # read by the attention kernel (fp32)
                 att = E.window_attention(qkv, pk["rel"], pk["heads"], pk["ws"], pk["shift"])
-                E.conv(pk["proj"], [att], b, L.EPI_ADD, r1=x)
+                E.conv(pk["proj"], [att], b, L.EPI_ADD, r1=x, fmt=fb)
             for r in pk["b"]:
-                b = self._ru(E, r, b)
+                b = self._ru(E, r, b, fmt=2)
             E.conv(pk["out"], [b], out, L.EPI_GATE, r1=x, r2=a)
         return out
 
     def _g_a_one(self, E: Engine, pk, x: Tensor, out: Act) -> Act:
         """CHProg_cnn.py:131-144."""
         with E.scope():
-            # fmt: a conv feeding a GDN is read as fp32 (x and x*x), a GDN feeding a conv is read as planes only
+            # a conv feeding a GDN writes fp32 x (the GDN's multiplier) and the planes of x*x (its operand); a GDN
+            # feeding a conv is read as planes only
             h = E.im2col_first(x, 5, 2, 2, 80)
-            h = E.conv_new(pk["c0"], [h], fmt=1)
+            h = E.conv_new(pk["c0"], [h], square_planes=True)
             h = E.gdn_new(pk["g1"], h, False, fmt=2)
-            h = E.conv_new(pk["c2"], [h], fmt=1)
+            h = E.conv_new(pk["c2"], [h], square_planes=True)
             h = E.gdn_new(pk["g3"], h, False)
             h = self._win(E, pk["w4"], h)
-            h = E.conv_new(pk["c5"], [h], fmt=1)
+            h = E.conv_new(pk["c5"], [h], square_planes=True)
             h = E.gdn_new(pk["g6"], h, False, fmt=2)
             h = E.conv_new(pk["c7"], [h])
             self._win(E, pk["w8"], h, out)
@@ -336,12 +341,12 @@ class ChannelProgresssiveWACNN(nn.Module):
         pk = P["g_s"][which if self.multiple_decoder else 0]
         with E.scope():
             h = self._win(E, pk["w0"], y_hat)
-            h = E.deconv_new(pk["d1"], h, fmt=1)
+            h = E.deconv_new(pk["d1"], h, square_planes=True)
             h = E.gdn_new(pk["g2"], h, True, fmt=2)
-            h = E.deconv_new(pk["d3"], h, fmt=1)
+            h = E.deconv_new(pk["d3"], h, square_planes=True)
             h = E.gdn_new(pk["g4"], h, True)
             h = self._win(E, pk["w5"], h)
-            h = E.deconv_new(pk["d6"], h, fmt=1)
+            h = E.deconv_new(pk["d6"], h, square_planes=True)
             h = E.gdn_new(pk["g7"], h, True, fmt=2)
             epi = L.EPI_CLAMP01 if clamp else L.EPI_LINEAR
             if isinstance(pk["d8"], PackedConv):  # merged sub-pixel phases, written straight to the NCHW image

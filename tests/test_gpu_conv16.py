@@ -216,3 +216,35 @@ def test_tc16_large_m_many_tiles():
     got = out.t.permute(0, 3, 1, 2)
     scale = ref.pow(2).mean().sqrt().item()
     assert (got - ref).abs().max().item() <= 8 * RTOL * scale
+
+
+def test_tc16_residual_from_planes_and_squared_planes_for_gdn():
+    """(a) a ResidualUnit-like chain whose tensors exist only as split planes: the 1x1 epilogue reads the residual operand
+    from the planes; (b) conv -> GDN where the conv's epilogue writes the planes of x*x, so the GDN launch needs no
+    separate squaring pass."""
+    from progressivecodec_b200 import _lib as L
+    from progressivecodec_b200.engine import pack_conv2d, pack_gdn
+    from progressivecodec_b200.layers import GDN
+    from progressivecodec_b200.synthetic import synthetic_tensor
+
+    E = _engine()
+    torch.manual_seed(2)
+    m0, m1 = nn.Conv2d(64, 192, 1), nn.Conv2d(192, 192, 1)
+    x = torch.randn(2, 64, 16, 24)
+    h0 = m0(x)
+    ref = F.gelu(m1(h0) + h0).detach()
+    p0, p1 = pack_conv2d(m0, E.device, "a").attach_tc(3), pack_conv2d(m1, E.device, "b").attach_tc(3)
+    a0 = E.conv_new(p0, [_nhwc(x)], fmt=2)          # planes only
+    assert a0.base == 0
+    out = E.conv_new(p1, [a0], L.EPI_ADD_GELU, r1=a0)
+    _close(_nchw(out), ref)
+    g = GDN(192)
+    with torch.no_grad():
+        g.beta.copy_(synthetic_tensor("g.beta", g.beta, 0))
+        g.gamma.copy_(synthetic_tensor("g.gamma", g.gamma, 0))
+    beta, gamma = g.effective()
+    hx = m0(x).detach()
+    refg = hx * torch.rsqrt(F.conv2d(hx * hx, gamma.reshape(192, 192, 1, 1), beta))
+    c = E.conv_new(p0, [_nhwc(x)], square_planes=True)
+    assert c._root.sq
+    _close(_nchw(E.gdn_new(pack_gdn(g, E.device, "g").attach_tc(), c, False)), refg)
