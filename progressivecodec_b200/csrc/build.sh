@@ -4,7 +4,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 OUT=../libpcodec_b200.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr"
+FLAGS="${PCODEC_EXPERIMENTS:+-DPCODEC_EXPERIMENTS} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr"
 OBJS=()
 for f in rans.cu entropy_ops.cu conv_simt.cu conv_tc.cu conv_tc16.cu attention.cu host.cpp; do
   o=build/${f%.*}.o

@@ -51,7 +51,7 @@ struct W16 {
 struct Plan16 {  // host side, stored in desc->plan
   uint32_t magic;
   int tw, th, tw_shift, tiles_w, tiles_h;
-  int bn, n_tiles, stages, n_hi, n_steps, smem;
+  int bn, n_tiles, stages, n_hi, n_lo, n_steps, n_ksteps, smem;
   unsigned char maps[10 * sizeof(CUtensorMap)];  // a_hi[4] | a_lo[4] | w_hi | w_lo
 };
 static_assert(sizeof(Plan16) <= PCODEC_CONV_PLAN_BYTES, "plan scratch too small");
@@ -61,7 +61,8 @@ struct alignas(64) Params16 {
   pcodec_conv_desc d;
   const float *w_scale;  // device: [1] = 2^-wshift
   int tw, th, tw_shift, tiles_w, tiles_h;
-  int bn, stages, n_hi, n_steps;
+  int bn, stages, n_hi, n_lo, n_steps, n_ksteps;
+  int debug;  // PCODEC_EXPERIMENTS builds only (timing experiments, wrong results): 1 = no A loads, 2 = no B loads, 4 = hi*hi MMAs only
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -141,6 +142,16 @@ __global__ void split_weights16_kernel(const float *__restrict__ w_tap_major, in
 // ---------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------
+#ifdef PCODEC_EXPERIMENTS
+// timeline of one CTA (PCODEC_TC16_DEBUG bit 6; bit 7: a mid-grid CTA): clock64 at
+//   0 kernel entry, 1 setup done (barriers, TMEM), 2 first stage landed, 3 last MMA committed (issuer), 4 accumulators
+//   complete (epilogue warps released), 5 epilogue done, 6 kernel exit; 8+s: MMA issue of slab s (s < 100)
+__device__ long long g_trace16[128];
+#define T16(ev) do { if (trace) g_trace16[ev] = clock64(); } while (0)
+#else
+#define T16(ev) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(32 * NWARPS, 2)
 conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -166,7 +177,11 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
   const uint32_t tmem_slot = tmem_full + 8u;
   uint8_t *smem_gen = smem_raw;
 
-  const int n_acc = P.n_hi + 1;  // hi accumulators (round-robin over K slabs) + the lo accumulator
+#ifdef PCODEC_EXPERIMENTS
+  const bool trace = (P.debug & 64) && blockIdx.x == ((P.debug & 128) ? gridDim.x / 2 : 0) && blockIdx.y == 0 && lane == 0;
+#endif
+  if (warp == 2) T16(0);
+  const int n_acc = P.n_hi + P.n_lo;  // hi accumulators + lo accumulators, both used round-robin over the K steps
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < n_acc * bn) tmem_cols <<= 1;
 
@@ -183,6 +198,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+  if (warp == 2) T16(1);
 
   // tile = th x tw block of output-grid pixels of one image
   int t = blockIdx.x;
@@ -200,14 +216,26 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       uint32_t ph = 1;
       for (int s = 0; s < n_steps; ++s) {
         mbar_wait(empty(st), ph);
-        mbar_expect_tx(full(st), (uint32_t)stage_bytes);
         const int c = kc * KS;
         const int x = w0 * d.in_step + d.dx[tap], y = h0 * d.in_step + d.dy[tap];
+        const int k = tap * d.cin_total + seg_cbase + c;
+#ifdef PCODEC_EXPERIMENTS
+        mbar_expect_tx(full(st), (uint32_t)(((P.debug & 1) ? 0 : 2 * A_BYTES) + ((P.debug & 2) ? 0 : 2 * b_bytes)));
+        if (!(P.debug & 1)) {
+          tma_load_4d(a_hi(st), &P.a_hi[seg], full(st), c, x, y, img);
+          tma_load_4d(a_lo(st), &P.a_lo[seg], full(st), c, x, y, img);
+        }
+        if (!(P.debug & 2)) {
+          tma_load_2d(b_hi(st), &P.w_hi, full(st), k, n0);
+          tma_load_2d(b_lo(st), &P.w_lo, full(st), k, n0);
+        }
+#else
+        mbar_expect_tx(full(st), (uint32_t)stage_bytes);
         tma_load_4d(a_hi(st), &P.a_hi[seg], full(st), c, x, y, img);
         tma_load_4d(a_lo(st), &P.a_lo[seg], full(st), c, x, y, img);
-        const int k = tap * d.cin_total + seg_cbase + c;
         tma_load_2d(b_hi(st), &P.w_hi, full(st), k, n0);
         tma_load_2d(b_lo(st), &P.w_lo, full(st), k, n0);
+#endif
         const int sc = d.seg[seg].channels;
         if (++kc == (sc + KS - 1) / KS) {
           kc = 0;
@@ -221,25 +249,41 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
     // =============================== MMA issuer ===============================
     // instruction descriptor: D = f32 (1 << 4), A = B = f16 (format 0), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t acc_lo = tmem_acc + (uint32_t)(P.n_hi * bn);
+    // Consecutive MMAs into the SAME accumulator serialise on the tensor core's accumulate latency (~100 clk: the
+    // N/2-clk instructions of a narrow tile ran 2-6x below their issue rate when hi / lo / lo hit two accumulators).
+    // The K steps therefore round-robin over n_hi hi and n_lo lo accumulators: every accumulator still sees a fixed
+    // sequence of products (deterministic), and the epilogue adds them up with round-to-nearest.
+    const uint32_t lo_base = tmem_acc + (uint32_t)(P.n_hi * bn);
     if (elect_one()) {
-      int seg = 0, tap = 0, kc = 0, st = 0, hi_idx = 0;
-      uint32_t ph = 0;
+      int seg = 0, tap = 0, kc = 0, st = 0, hi_idx = 0, lo_idx = 0;
+      uint32_t ph = 0, hi_init = 0, lo_init = 0;
+      const int n_hi = P.n_hi, n_lo = P.n_lo;
       for (int s = 0; s < n_steps; ++s) {
         const int sc = d.seg[seg].channels;
         const int ksteps = (min(KS, sc - kc * KS) + 15) >> 4;  // K steps of 16 channels that hold data (the rest is zero fill)
         mbar_wait(full(st), ph);
         tc_fence_after();
+#ifdef PCODEC_EXPERIMENTS
+        if (s == 0) T16(2);
+        if (s < 100) T16(8 + s);
+#endif
         const uint64_t da_hi = umma_desc_sw128(a_hi(st)), da_lo = umma_desc_sw128(a_lo(st));
         const uint64_t db_hi = umma_desc_sw128(b_hi(st)), db_lo = umma_desc_sw128(b_lo(st));
-        const uint32_t acc_hi = tmem_acc + (uint32_t)(hi_idx * bn);
-        const bool first_hi = s < P.n_hi;
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units inside the swizzle row
-          umma_f16_ss(acc_hi, da_hi + adv, db_hi + adv, idesc, (!first_hi || k > 0) ? 1u : 0u);
-          umma_f16_ss(acc_lo, da_lo + adv, db_hi + adv, idesc, (s > 0 || k > 0) ? 1u : 0u);
-          umma_f16_ss(acc_lo, da_hi + adv, db_lo + adv, idesc, 1u);
+          umma_f16_ss(tmem_acc + (uint32_t)(hi_idx * bn), da_hi + adv, db_hi + adv, idesc, (hi_init >> hi_idx) & 1u);
+          hi_init |= 1u << hi_idx;
+          if (++hi_idx == n_hi) hi_idx = 0;
+#ifdef PCODEC_EXPERIMENTS
+          if (P.debug & 4) continue;
+#endif
+          umma_f16_ss(lo_base + (uint32_t)(lo_idx * bn), da_lo + adv, db_hi + adv, idesc, (lo_init >> lo_idx) & 1u);
+          lo_init |= 1u << lo_idx;
+          if (++lo_idx == n_lo) lo_idx = 0;
+          umma_f16_ss(lo_base + (uint32_t)(lo_idx * bn), da_hi + adv, db_lo + adv, idesc, (lo_init >> lo_idx) & 1u);
+          lo_init |= 1u << lo_idx;
+          if (++lo_idx == n_lo) lo_idx = 0;
         }
         umma_commit(empty(st));
         if (++kc == (sc + KS - 1) / KS) {
@@ -247,9 +291,9 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
           if (++tap == d.n_taps) { tap = 0; ++seg; }
         }
         if (++st == stages) { st = 0; ph ^= 1u; }
-        if (++hi_idx == P.n_hi) hi_idx = 0;
       }
       umma_commit(tmem_full);
+      T16(3);
     }
     __syncwarp();
   } else {
@@ -301,9 +345,11 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (warp == 2) T16(4);
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    const int n_hi_used = min(P.n_hi, n_steps);  // short reductions touch fewer hi accumulators
-    // acc[16] <- (sum of the hi accumulators + 2^-11 * lo accumulator) * 2^-wshift for columns c0 .. c0+15
+    const int n_hi_used = min(P.n_hi, P.n_ksteps);      // very short reductions touch fewer accumulators
+    const int n_lo_used = min(P.n_lo, 2 * P.n_ksteps);
+    // acc[16] <- (sum of the hi accumulators + 2^-11 * sum of the lo accumulators) * 2^-wshift for columns c0 .. c0+15
     auto load_acc = [&](int c0, float (&acc)[16]) {
       uint32_t t0[16], t1[16];
       tmem_ld16_issue(lane_addr + (uint32_t)c0, t0);
@@ -311,17 +357,28 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       tmem_wait_ld();
       tmem_pin(t0);
       tmem_pin(t1);
+      float lo[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(t0[j]);
+      for (int j = 0; j < 16; ++j) { acc[j] = __uint_as_float(t0[j]); lo[j] = __uint_as_float(t1[j]); }
 #pragma unroll 1
-      for (int a = 1; a < n_hi_used; ++a) {
-        float part[16];
-        tmem_ld16(lane_addr + (uint32_t)(a * bn + c0), part);
+      for (int a = 1; a < max(n_hi_used, n_lo_used); ++a) {
+        const bool h = a < n_hi_used, l = a < n_lo_used;  // warp-uniform
+        if (h) tmem_ld16_issue(lane_addr + (uint32_t)(a * bn + c0), t0);
+        if (l) tmem_ld16_issue(lane_addr + (uint32_t)((P.n_hi + a) * bn + c0), t1);
+        tmem_wait_ld();
+        if (h) {
+          tmem_pin(t0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += part[j];
+          for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(t0[j]);
+        }
+        if (l) {
+          tmem_pin(t1);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) lo[j] += __uint_as_float(t1[j]);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = __fmul_rn(__fmaf_rn(__uint_as_float(t1[j]), LO_INV, acc[j]), out_scale);
+      for (int j = 0; j < 16; ++j) acc[j] = __fmul_rn(__fmaf_rn(lo[j], LO_INV, acc[j]), out_scale);
     };
 
     if (d.flags & PCODEC_FLAG_SUBPIXEL_NCHW) {
@@ -463,12 +520,14 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       }
     }
     tc_fence_before();
+    if (warp == 2) T16(5);
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, tmem_cols);
   }
+  if (warp == 2) T16(6);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -500,28 +559,51 @@ int max_mma_per_acc() {
 // accumulator for no hi accumulator to see more than max_mma_per_acc() MMAs.  Short reductions (<= 24 hi MMAs, i.e. the
 // 1x1 layers) spend most of a tile's life in its serial prologue / epilogue: they get tiles of <= 128 columns with ONE hi
 // accumulator (<= 256 TMEM columns) so that two CTAs share an SM and overlap each other.
-int pick_bn16(int cout, int n_mma_hi, int *n_hi_out) {
+int pick_bn16(int cout, int n_mma_hi, int *n_hi_out, int *n_lo_out) {
   if (cout % 16 != 0) return 0;
   static const bool pair_short = [] { const char *e = getenv("PCODEC_TC16_PAIR"); return !e || atoi(e) != 0; }();
+  static const int lo_max = [] { const char *e = getenv("PCODEC_TC16_NLO"); return e ? std::max(1, std::min(4, atoi(e))) : 4; }();
+  auto finish = [&](int bn, int cols, int need) {
+    // spend the TMEM columns next to `need` hi accumulators on lo accumulators (2 break the lo -> lo dependency, narrow
+    // tiles want more), then on further hi accumulators
+    int n_lo = std::min(lo_max, bn <= 64 ? 4 : 2);
+    while (n_lo > 1 && (need + n_lo) * bn > cols) --n_lo;
+    *n_lo_out = n_lo;
+    *n_hi_out = std::max(need, std::min(4, cols / bn - n_lo));
+    return bn;
+  };
   if (pair_short && n_mma_hi <= 24) {
     for (int tiles = 1; tiles <= 64; ++tiles) {
       int bn = (cout + tiles - 1) / tiles;
       bn = (bn + 15) & ~15;
       if (bn > 128) continue;
-      *n_hi_out = 1;
-      return bn;
+      return finish(bn, 256, 1);
     }
   }
-  const int need = std::min(4, std::max(1, (n_mma_hi + max_mma_per_acc() - 1) / max_mma_per_acc()));
-  for (int relax = need; relax >= 1; --relax) {
+  // long reductions: fewest N tiles first (every extra tile is another pass over A); within a tile width, two lo
+  // accumulators when the hi accumulators next to them stay under 1.25 x the MMA bound, else one
+  for (int pass = 0; pass < 2; ++pass)
     for (int tiles = 1; tiles <= 64; ++tiles) {
       int bn = (cout + tiles - 1) / tiles;
       bn = (bn + 15) & ~15;
-      if (bn > 256 || (relax + 1) * bn > 512) continue;
-      *n_hi_out = std::min(4, 512 / bn - 1);
-      return bn;
+      if (bn > 256) continue;
+      const int total = std::min(8, 512 / bn);
+      if (total < 2) continue;
+      if (total >= 3 && lo_max >= 2) {
+        const int n_hi = std::min(4, total - 2);
+        if (pass == 1 || 4 * n_mma_hi <= 5 * n_hi * max_mma_per_acc()) {
+          *n_hi_out = n_hi;
+          *n_lo_out = std::min(lo_max, bn <= 64 ? std::min(4, total - n_hi) : 2);
+          return bn;
+        }
+      }
+      const int n_hi = std::min(4, total - 1);
+      if (pass == 1 || n_mma_hi <= n_hi * max_mma_per_acc()) {
+        *n_hi_out = n_hi;
+        *n_lo_out = 1;
+        return bn;
+      }
     }
-  }
   return 0;
 }
 
@@ -578,6 +660,13 @@ void pcodec_tc16_weights_destroy(void *handle) {
 }
 
 const void *pcodec_tc_w16(const void *tc_weights);  // conv_tc.cu: the fp16 weights behind a pcodec_conv_tc_prepare handle
+
+#ifdef PCODEC_EXPERIMENTS
+extern "C" int pcodec_debug_tc16_trace(long long *out, int n) {
+  if (!out || n < 128) return 128;
+  return cudaMemcpyFromSymbol(out, g_trace16, sizeof(long long) * 128) == cudaSuccess ? 128 : -1;
+}
+#endif
 
 extern "C" int pcodec_split_planes(const float *src, int src_ps, int64_t n_pixels, int channels, uint16_t *hi, uint16_t *lo,
                                    int dst_ps, int square, void *stream) {
@@ -657,13 +746,14 @@ extern "C" int pcodec_conv_plan(pcodec_conv_desc *desc) {
     n_mma_hi += desc->n_taps * ((ch + 15) / 16);
   }
   pl->n_steps = n_steps;
-  pl->bn = pick_bn16(desc->cout, n_mma_hi, &pl->n_hi);
+  pl->bn = pick_bn16(desc->cout, n_mma_hi, &pl->n_hi, &pl->n_lo);
+  pl->n_ksteps = n_mma_hi;
   if (pl->bn == 0) return PCODEC_ERR_UNSUPPORTED;
   pl->n_tiles = (desc->cout + pl->bn - 1) / pl->bn;
   const int stage_bytes = 2 * A_BYTES + 2 * pl->bn * 128;
   auto need = [&](int st) { return std::max(st * stage_bytes, EPI_WARPS * 2048) + 8 * (2 * st + 2) + 64; };
   int tmem_cols = 32;
-  while (tmem_cols < (pl->n_hi + 1) * pl->bn) tmem_cols <<= 1;
+  while (tmem_cols < (pl->n_hi + pl->n_lo) * pl->bn) tmem_cols <<= 1;
   // tiles of <= 256 TMEM columns: keep the footprint small enough for TWO resident CTAs (one's prologue / epilogue
   // overlaps the other's main loop); wider tiles take the whole SM and as many stages as fit
   const int limit = (tmem_cols <= 256 && need(1) <= SMEM_HALF) ? SMEM_HALF : SMEM_LIMIT;
@@ -730,10 +820,15 @@ int pcodec_conv_taps_tc16(const pcodec_conv_desc *desc, void *stream) {
   P.d = *desc;
   P.w_scale = w->dev_scale;
   P.tw = pl->tw; P.th = pl->th; P.tw_shift = pl->tw_shift; P.tiles_w = pl->tiles_w; P.tiles_h = pl->tiles_h;
-  P.bn = pl->bn; P.stages = pl->stages; P.n_hi = pl->n_hi; P.n_steps = pl->n_steps;
+  P.bn = pl->bn; P.stages = pl->stages; P.n_hi = pl->n_hi; P.n_lo = pl->n_lo; P.n_steps = pl->n_steps;
+  P.n_ksteps = pl->n_ksteps;
+  P.debug = 0;
+#ifdef PCODEC_EXPERIMENTS
+  if (const char *e = getenv("PCODEC_TC16_DEBUG")) P.debug = atoi(e);
+#endif
   if (getenv("PCODEC_TC_VERBOSE"))
-    fprintf(stderr, "[conv_tc16] grid %dx%d tile %dx%d bn=%d n_tiles=%d n_steps=%d stages=%d n_hi=%d smem=%d\n", desc->grid_h,
-            desc->grid_w, pl->th, pl->tw, pl->bn, pl->n_tiles, pl->n_steps, pl->stages, pl->n_hi, pl->smem);
+    fprintf(stderr, "[conv_tc16] grid %dx%d tile %dx%d bn=%d n_tiles=%d n_steps=%d stages=%d n_hi=%d n_lo=%d smem=%d\n", desc->grid_h,
+            desc->grid_w, pl->th, pl->tw, pl->bn, pl->n_tiles, pl->n_steps, pl->stages, pl->n_hi, pl->n_lo, pl->smem);
   {
     static std::atomic<uint64_t> attr_mask{0};
     uint64_t bit;
