@@ -148,30 +148,32 @@ def run_reference(args):
 # our arm
 # ----------------------------------------------------------------------------------------------------------
 def conv_roofline(net, peaks, peak_kind):
-    """Dominant kernel = the tap-GEMM convolution.  Time it alone (CUDA events on the launch stream, L2 flushed
-    between launches) on the layer that carries most FLOPs of the transforms: 5x5 stride-2 conv 192->192 at
-    256x384 -> 128x192 (45.3 GFLOP, g_a[2])."""
+    """Dominant kernel = the tap-GEMM convolution (conv_taps_tc16_kernel: fp16-split tcgen05, both operands by TMA).
+    Time it alone (CUDA events on the launch stream, L2 flushed between launches) on the layer that carries most FLOPs
+    of the transforms: 5x5 stride-2 conv 192->192 at 256x384 -> 128x192 (45.3 GFLOP per image, g_a[2])."""
     import torch
 
-    from progressivecodec_b200.engine import Act, new_act
+    from progressivecodec_b200.engine import Act
 
     P = net.prepare()
     E = P["eng"]
     E.begin(0)  # latch the CURRENT stream for this thread's launches (the CUDA events below are recorded on it)
     pc = P["g_a"][0]["c2"]
-    nb = 8  # images per launch: 3072 CTAs = 20.8 waves of 148, as in the batched run (one image is 2.6 waves)
+    nb = 8  # images per launch: 2 x 3072 CTAs (two N tiles), as in the batched run
     x = Act(torch.randn(nb, 256, 384, 192, device=E.device))
-    out = new_act(nb, 128, 192, 192, E.device)
+    if E.planes(x) is None:  # the operand format of the kernel: split-fp16 planes (written by the producer's epilogue
+        raise RuntimeError("roofline launch: no planes")  # in the model; converted once here, outside the timed region)
+    out = E.act(nb, 128, 192, 192, fmt=1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=E.device)
     flops = 2.0 * nb * 128 * 192 * 192 * (25 * 192)
     for _ in range(3):
-        E.conv(pc, [x], out)
+        E.conv(pc, [x], out, fmt=1)
     times = []
     for _ in range(10):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        E.conv(pc, [x], out)
+        E.conv(pc, [x], out, fmt=1)
         e1.record()
         e1.synchronize()
         times.append(e0.elapsed_time(e1) * 1e-3)
@@ -180,19 +182,20 @@ def conv_roofline(net, peaks, peak_kind):
     peak = peaks["bf16_tflops"]
     # DRAM traffic of this exact launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set
     # full` capture of tools/prof_conv_one.py, recorded in profiles/roofline_traffic.json; null if not captured.
-    # Algorithmic bytes = NHWC input + TF32 hi/lo weights + output.
+    # Algorithmic bytes = input planes (hi + lo fp16 = 4 B / element) + fp16 hi/lo weights + fp32 output.
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.isfile(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    alg_bytes = 4.0 * (nb * 256 * 384 * 192 + 2 * 25 * 192 * 192 + nb * 128 * 192 * 192)
-    return {"bound": "tensor", "kernel": f"conv_taps_tc_kernel (tcgen05 3xTF32; 5x5 s2 192->192, {nb} x 256x384 -> 128x192)",
+    alg_bytes = 4.0 * (nb * 256 * 384 * 192 + 25 * 192 * 192 + nb * 128 * 192 * 192)
+    return {"bound": "tensor",
+            "kernel": f"conv_taps_tc16_kernel (tcgen05 kind::f16, fp16-split operands by TMA; 5x5 s2 192->192, {nb} x 256x384 -> 128x192)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes": alg_bytes,
-            "peak_kind": peak_kind + " bf16 burst (cuBLAS); this kernel issues 3 TF32 MMAs per algorithmic MAC, "
-                         "TF32 runs at half the bf16 rate, so frac <= 1/6",
-            "tensor_pipe_frac_of_tf32_peak": 3.0 * achieved / (peak / 2.0),
+            "peak_kind": peak_kind + " bf16 burst (cuBLAS); this kernel issues 3 fp16 MMAs per algorithmic MAC (hi*hi, "
+                         "lo*hi, hi*lo: fp32-class results, which the entropy stage needs), so frac <= 1/3",
+            "tensor_pipe_frac_of_f16_peak": 3.0 * achieved / peak,
             "flops_per_launch": flops, "avg_launch_ms": avg * 1e3}
 
 

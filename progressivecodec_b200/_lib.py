@@ -9,7 +9,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpcodec_b200.so")
+LIB_PATH = os.environ.get("PCODEC_LIB") or os.path.join(HERE, "libpcodec_b200.so")  # (PCODEC_LIB: bisecting builds)
 
 MAX_SEGMENTS = 4
 MAX_TAPS = 25

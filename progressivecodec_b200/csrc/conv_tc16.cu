@@ -51,7 +51,7 @@ struct W16 {
 struct Plan16 {  // host side, stored in desc->plan
   uint32_t magic;
   int tw, th, tw_shift, tiles_w, tiles_h;
-  int bn, n_tiles, stages, n_hi, n_lo, n_steps, n_ksteps, smem;
+  int bn, n_tiles, stages, n_hi, n_lo, n_steps, n_ksteps, smem, ts;
   unsigned char maps[10 * sizeof(CUtensorMap)];  // a_hi[4] | a_lo[4] | w_hi | w_lo
 };
 static_assert(sizeof(Plan16) <= PCODEC_CONV_PLAN_BYTES, "plan scratch too small");
@@ -62,6 +62,7 @@ struct alignas(64) Params16 {
   const float *w_scale;  // device: [1] = 2^-wshift
   int tw, th, tw_shift, tiles_w, tiles_h;
   int bn, stages, n_hi, n_lo, n_steps, n_ksteps;
+  int ts;     // 1: the A slices go shared -> tensor memory with tcgen05.cp and the MMAs take A from TMEM (TS form)
   int debug;  // PCODEC_EXPERIMENTS builds only (timing experiments, wrong results): 1 = no A loads, 2 = no B loads, 4 = hi*hi MMAs only
 };
 
@@ -183,9 +184,14 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
   if (warp == 2) T16(0);
   const int n_acc = P.n_hi + P.n_lo;  // hi accumulators + lo accumulators, both used round-robin over the K steps
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < n_acc * bn) tmem_cols <<= 1;
+  while ((int)tmem_cols < n_acc * bn + (P.ts ? 64 : 0)) tmem_cols <<= 1;
 
-  if (warp == 1 && lane == 0) {
+  if (warp == 0 && lane == 0) {
+    // the TMA unit fetches each 128-byte tensor map on first use: start those fetches before anything else
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.a_hi[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.a_lo[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.w_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.w_lo) : "memory");
     for (int s = 0; s < stages; ++s) {
       mbar_init(full(s), 1);
       mbar_init(empty(s), 1);
@@ -193,6 +199,8 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
+  // tcgen05.alloc is .sync.aligned: the WHOLE warp must arrive converged, so it runs in a warp that has not diverged
+  // (the barrier initialisation by a single lane lives in warp 0 for that reason)
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -215,7 +223,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       int seg = 0, tap = 0, kc = 0, seg_cbase = 0, st = 0;
       uint32_t ph = 1;
       for (int s = 0; s < n_steps; ++s) {
-        mbar_wait(empty(st), ph);
+        if (P.debug & 512) mbar_wait(empty(st), ph); else mbar_wait_spin(empty(st), ph);
         const int c = kc * KS;
         const int x = w0 * d.in_step + d.dx[tap], y = h0 * d.in_step + d.dy[tap];
         const int k = tap * d.cin_total + seg_cbase + c;
@@ -249,11 +257,11 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
     // =============================== MMA issuer ===============================
     // instruction descriptor: D = f32 (1 << 4), A = B = f16 (format 0), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    // Consecutive MMAs into the SAME accumulator serialise on the tensor core's accumulate latency (~100 clk: the
-    // N/2-clk instructions of a narrow tile ran 2-6x below their issue rate when hi / lo / lo hit two accumulators).
-    // The K steps therefore round-robin over n_hi hi and n_lo lo accumulators: every accumulator still sees a fixed
-    // sequence of products (deterministic), and the epilogue adds them up with round-to-nearest.
+    // The K steps round-robin over n_hi hi and n_lo lo accumulators: every accumulator sees a fixed sequence of products
+    // (deterministic), and the epilogue adds them up with round-to-nearest.  (Several lo accumulators were tried against
+    // the idea that back-to-back MMAs into one accumulator serialise: no change, so n_lo = 1 by default.)
     const uint32_t lo_base = tmem_acc + (uint32_t)(P.n_hi * bn);
+    const uint32_t a_tmem = tmem_acc + (uint32_t)(n_acc * bn);  // TS form: 4 K steps x (hi 8 + lo 8) columns
     if (elect_one()) {
       int seg = 0, tap = 0, kc = 0, st = 0, hi_idx = 0, lo_idx = 0;
       uint32_t ph = 0, hi_init = 0, lo_init = 0;
@@ -261,7 +269,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       for (int s = 0; s < n_steps; ++s) {
         const int sc = d.seg[seg].channels;
         const int ksteps = (min(KS, sc - kc * KS) + 15) >> 4;  // K steps of 16 channels that hold data (the rest is zero fill)
-        mbar_wait(full(st), ph);
+        if (P.debug & 512) mbar_wait(full(st), ph); else mbar_wait_spin(full(st), ph);
         tc_fence_after();
 #ifdef PCODEC_EXPERIMENTS
         if (s == 0) T16(2);
@@ -272,6 +280,24 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units inside the swizzle row
+          if (P.ts) {
+            // The SS form re-reads the 128-row A slice from shared memory for every MMA: 32 bytes out of each 128-byte row,
+            // ~100 clk of shared-memory wavefronts whatever N — more than the N/2 clk of a narrow tile's MMA (measured:
+            // 83 clk per MMA at N = 112, 107 at N = 32).  Copy each slice ONCE into tensor memory and use the TS form.
+            const uint32_t ta_hi = a_tmem + (uint32_t)(k * 16), ta_lo = ta_hi + 8u;
+            tmem_cp_128x256b(ta_hi, da_hi + adv);
+            tmem_cp_128x256b(ta_lo, da_lo + adv);
+            umma_f16_ts(tmem_acc + (uint32_t)(hi_idx * bn), ta_hi, db_hi + adv, idesc, (hi_init >> hi_idx) & 1u);
+            hi_init |= 1u << hi_idx;
+            if (++hi_idx == n_hi) hi_idx = 0;
+            umma_f16_ts(lo_base + (uint32_t)(lo_idx * bn), ta_lo, db_hi + adv, idesc, (lo_init >> lo_idx) & 1u);
+            lo_init |= 1u << lo_idx;
+            if (++lo_idx == n_lo) lo_idx = 0;
+            umma_f16_ts(lo_base + (uint32_t)(lo_idx * bn), ta_hi, db_lo + adv, idesc, (lo_init >> lo_idx) & 1u);
+            lo_init |= 1u << lo_idx;
+            if (++lo_idx == n_lo) lo_idx = 0;
+            continue;
+          }
           umma_f16_ss(tmem_acc + (uint32_t)(hi_idx * bn), da_hi + adv, db_hi + adv, idesc, (hi_init >> hi_idx) & 1u);
           hi_init |= 1u << hi_idx;
           if (++hi_idx == n_hi) hi_idx = 0;
@@ -559,10 +585,13 @@ int max_mma_per_acc() {
 // accumulator for no hi accumulator to see more than max_mma_per_acc() MMAs.  Short reductions (<= 24 hi MMAs, i.e. the
 // 1x1 layers) spend most of a tile's life in its serial prologue / epilogue: they get tiles of <= 128 columns with ONE hi
 // accumulator (<= 256 TMEM columns) so that two CTAs share an SM and overlap each other.
-int pick_bn16(int cout, int n_mma_hi, int *n_hi_out, int *n_lo_out) {
+int pick_bn16(int cout, int n_mma_hi, int *n_hi_out, int *n_lo_out, int ts) {
   if (cout % 16 != 0) return 0;
+  const int cols_full = ts ? 448 : 512, cols_pair = ts ? 192 : 256;  // TS form: 64 columns hold the A slices
   static const bool pair_short = [] { const char *e = getenv("PCODEC_TC16_PAIR"); return !e || atoi(e) != 0; }();
-  static const int lo_max = [] { const char *e = getenv("PCODEC_TC16_NLO"); return e ? std::max(1, std::min(4, atoi(e))) : 4; }();
+  // one lo accumulator by default: a second one measured no faster (back-to-back MMAs into one accumulator are not the
+  // bound) and costs the long reductions a hi accumulator, i.e. accuracy; PCODEC_TC16_NLO keeps the experiment reachable
+  static const int lo_max = [] { const char *e = getenv("PCODEC_TC16_NLO"); return e ? std::max(1, std::min(4, atoi(e))) : 1; }();
   auto finish = [&](int bn, int cols, int need) {
     // spend the TMEM columns next to `need` hi accumulators on lo accumulators (2 break the lo -> lo dependency, narrow
     // tiles want more), then on further hi accumulators
@@ -576,8 +605,8 @@ int pick_bn16(int cout, int n_mma_hi, int *n_hi_out, int *n_lo_out) {
     for (int tiles = 1; tiles <= 64; ++tiles) {
       int bn = (cout + tiles - 1) / tiles;
       bn = (bn + 15) & ~15;
-      if (bn > 128) continue;
-      return finish(bn, 256, 1);
+      if (bn > cols_pair / 2) continue;
+      return finish(bn, cols_pair, 1);
     }
   }
   // long reductions: fewest N tiles first (every extra tile is another pass over A); within a tile width, two lo
@@ -587,7 +616,7 @@ int pick_bn16(int cout, int n_mma_hi, int *n_hi_out, int *n_lo_out) {
       int bn = (cout + tiles - 1) / tiles;
       bn = (bn + 15) & ~15;
       if (bn > 256) continue;
-      const int total = std::min(8, 512 / bn);
+      const int total = std::min(8, cols_full / bn);
       if (total < 2) continue;
       if (total >= 3 && lo_max >= 2) {
         const int n_hi = std::min(4, total - 2);
@@ -746,14 +775,16 @@ extern "C" int pcodec_conv_plan(pcodec_conv_desc *desc) {
     n_mma_hi += desc->n_taps * ((ch + 15) / 16);
   }
   pl->n_steps = n_steps;
-  pl->bn = pick_bn16(desc->cout, n_mma_hi, &pl->n_hi, &pl->n_lo);
+  static const int ts_default = [] { const char *e = getenv("PCODEC_TC16_TS"); return e ? atoi(e) : 0; }();
+  pl->ts = ts_default;
+  pl->bn = pick_bn16(desc->cout, n_mma_hi, &pl->n_hi, &pl->n_lo, pl->ts);
   pl->n_ksteps = n_mma_hi;
   if (pl->bn == 0) return PCODEC_ERR_UNSUPPORTED;
   pl->n_tiles = (desc->cout + pl->bn - 1) / pl->bn;
   const int stage_bytes = 2 * A_BYTES + 2 * pl->bn * 128;
   auto need = [&](int st) { return std::max(st * stage_bytes, EPI_WARPS * 2048) + 8 * (2 * st + 2) + 64; };
   int tmem_cols = 32;
-  while (tmem_cols < (pl->n_hi + pl->n_lo) * pl->bn) tmem_cols <<= 1;
+  while (tmem_cols < (pl->n_hi + pl->n_lo) * pl->bn + (pl->ts ? 64 : 0)) tmem_cols <<= 1;
   // tiles of <= 256 TMEM columns: keep the footprint small enough for TWO resident CTAs (one's prologue / epilogue
   // overlaps the other's main loop); wider tiles take the whole SM and as many stages as fit
   const int limit = (tmem_cols <= 256 && need(1) <= SMEM_HALF) ? SMEM_HALF : SMEM_LIMIT;
@@ -822,7 +853,9 @@ int pcodec_conv_taps_tc16(const pcodec_conv_desc *desc, void *stream) {
   P.tw = pl->tw; P.th = pl->th; P.tw_shift = pl->tw_shift; P.tiles_w = pl->tiles_w; P.tiles_h = pl->tiles_h;
   P.bn = pl->bn; P.stages = pl->stages; P.n_hi = pl->n_hi; P.n_lo = pl->n_lo; P.n_steps = pl->n_steps;
   P.n_ksteps = pl->n_ksteps;
+  P.ts = pl->ts;
   P.debug = 0;
+  if (getenv("PCODEC_TC16_SLEEPWAIT")) P.debug |= 512;  // (A/B knob: suspending try_wait in the producer / issuer threads)
 #ifdef PCODEC_EXPERIMENTS
   if (const char *e = getenv("PCODEC_TC16_DEBUG")) P.debug = atoi(e);
 #endif

@@ -33,6 +33,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity), "r"(0x989680)
       : "memory");
 }
+// Busy-poll variant for the single producer / issuer threads of a pipeline: mbarrier.test_wait never suspends the thread,
+// so the reaction to a completed phase is a few cycles instead of a wake-up.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "SPIN_LOOP:\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@!P1 bra SPIN_LOOP;\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
 // exact m / d for m < 2^31 with magic = ceil(2^(31+shift) / d), shift = ceil(log2 d)  (Granlund-Montgomery, N = 31):
 // the tile's pixel coordinates cost 2 multiplies per row instead of 2 integer divisions (~40 instructions each), which
 // was ~2 us of every tile's prologue
@@ -251,6 +263,23 @@ static __device__ __noinline__ F8 tc_epilogue8(int epi, F8 v, F8 r1, F8 r2, bool
   }
 #undef PC_EACH8
   return o;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem], kind::f16, M=128, K=16 (TS form): A = 128 lanes x 8 columns (two fp16 per column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared memory -> tensor memory, 128 rows x 256 bits (one K = 16 step of an fp16 A operand): row r -> lane r, 8 columns.
+// Executes in issue order with the tcgen05.mma of the same thread.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t smem_desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
 }
 
 }  // namespace pcodec_tc
