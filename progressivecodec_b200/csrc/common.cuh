@@ -55,6 +55,19 @@ static inline bool pcodec_device_needs(std::atomic<uint64_t> &mask, uint64_t *bi
     if (e__ != cudaSuccess) return -(int)e__;        \
   } while (0)
 
+// Experiment knobs (tiling, accumulator counts, pipeline variants) change rounding or are outright wrong-result timing
+// modes: a stray environment variable on only the encoder or only the decoder host would desynchronise the entropy
+// decoder silently.  They exist only in PCODEC_EXPERIMENTS builds (tools/exp_tc16.sh); release builds ignore them.
+#include <stdlib.h>
+static inline const char *pcodec_knob(const char *name) {
+#ifdef PCODEC_EXPERIMENTS
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -646,7 +646,7 @@ __global__ void split_weights_kernel(const float *__restrict__ w_tap_major, int 
 // columns >= cout).
 int pick_bn(int cout, int k_total, int cap = 256, int tmem_cols = 512) {
   if (cout % 16 != 0) return 0;
-  if (const char *e = getenv("PCODEC_TC_BNCAP")) cap = atoi(e);  // experiment knob
+  if (const char *e = pcodec_knob("PCODEC_TC_BNCAP")) cap = atoi(e);  // experiment knob
   const int n_steps = (k_total + TC_BK - 1) / TC_BK;
   const int need_hi = std::max(1, (4 * n_steps + 319) / 320);
   for (int tiles = 1; tiles <= 64; ++tiles) {
@@ -674,7 +674,7 @@ extern "C" int pcodec_conv_tc_prepare(const float *w_tap_major, int n_taps, int 
   // every cout <= 64 layer, 2 = also every 1-tap short reduction (separate lo accumulator, bn <= 64), 3 = as 2 with the
   // shared accumulator (bn <= 128).
   int mode = -1;
-  if (const char *e = getenv("PCODEC_TC_SMALL")) mode = atoi(e);
+  if (const char *e = pcodec_knob("PCODEC_TC_SMALL")) mode = atoi(e);
   const bool short_1tap = n_taps == 1 && n_slabs <= 24;
   bool small = mode < 0 ? (short_1tap && cout <= 128) : ((mode >= 1 && cout <= 64) || (mode >= 2 && short_1tap));
   const bool shared = small && short_1tap && (mode < 0 || mode >= 3);
@@ -788,12 +788,12 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   const int tmem_limit = h->small ? 256 : 512;
   int stages = 1;
   while (need(stages + 1) <= smem_limit && stages < 8) ++stages;
-  if (const char *e = getenv("PCODEC_TC_STAGES")) stages = std::min(stages, atoi(e));  // experiment knob
+  if (const char *e = pcodec_knob("PCODEC_TC_STAGES")) stages = std::min(stages, atoi(e));  // experiment knob
   if (stages > n_steps) stages = n_steps;
   if (stages < 1 || need(stages) > smem_limit) return PCODEC_ERR_UNSUPPORTED;
   P.stages = stages;
   P.debug = 0;
-  if (const char *e = getenv("PCODEC_TC_DEBUG")) P.debug = atoi(e);  // experiment knob (wrong results!)
+  if (const char *e = pcodec_knob("PCODEC_TC_DEBUG")) P.debug = atoi(e);  // experiment knob (wrong results!)
   {
     // TMEM columns: (n_hi hi accumulators + 1 lo) of bn columns + a_ring A operand buffers (hi 32 [+ lo 32] columns).
     // Prefer a 3-deep A ring; spend what is left on hi accumulators (up to 4).
@@ -805,7 +805,7 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
       ring = 2;
       n_acc = (tmem_limit - ring * a_cols) / h->bn;
     }
-    if (const char *e = getenv("PCODEC_TC_RING")) {  // experiment knob
+    if (const char *e = pcodec_knob("PCODEC_TC_RING")) {  // experiment knob
       ring = std::max(2, std::min(4, atoi(e)));
       n_acc = (tmem_limit - ring * a_cols) / h->bn;
     }
@@ -840,7 +840,7 @@ int pcodec_conv_taps_tc(const pcodec_conv_desc *desc, void *stream) {
   // PCODEC_TC_NG=3: a third converter group (18 warps).  EXPERIMENT, not yet run on hardware: with every load and TMEM
   // store switched off the slab period is still ~760 clk, i.e. the two groups' wait -> LDS -> store -> arrive cycle is
   // the floor of the long reductions (lesson 6).
-  static const bool three_groups = [] { const char *e = getenv("PCODEC_TC_NG"); return e && atoi(e) == 3; }();
+  static const bool three_groups = [] { const char *e = pcodec_knob("PCODEC_TC_NG"); return e && atoi(e) == 3; }();
   if (h->small)
     conv_taps_tc_kernel<1><<<grid, 32 * 10, smem, as_stream(stream)>>>(P, h->map_hi, h->map_lo);
   else if (three_groups && smem >= 16 * 2048 + 2048) {

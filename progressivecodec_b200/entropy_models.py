@@ -24,6 +24,7 @@ from torch import Tensor
 
 from . import _lib as L
 from . import ans as _ans
+from . import tables as _tables
 
 
 def _stream():
@@ -74,46 +75,34 @@ class EntropyModel(nn.Module):
         self.register_buffer("_cdf_length", torch.IntTensor())
         self._tables_cache = None
 
-    @property
-    def offset(self):
-        return self._offset
-
-    @property
-    def quantized_cdf(self):
-        return self._quantized_cdf
-
-    @property
-    def cdf_length(self):
-        return self._cdf_length
+    # read-only views of the table buffers (names of the reference's properties, entropy_models.py:102-120)
+    offset = property(lambda self: self._offset)
+    quantized_cdf = property(lambda self: self._quantized_cdf)
+    cdf_length = property(lambda self: self._cdf_length)
 
     # -- quantisation (entropy_models.py:126-165) ------------------------------------------------------
+    _MODES = ("noise", "dequantize", "symbols")
+
     def quantize(self, inputs: Tensor, mode: str, means: Optional[Tensor] = None) -> Tensor:
-        if mode not in ("noise", "dequantize", "symbols"):
+        """"symbols": int32 round(x - mean); "dequantize": round(x - mean) + mean; "noise": x + U(-1/2, 1/2) (training).
+        Host-tensor API of the reference; the model path does this inside pcodec_slice_quantize."""
+        if mode not in self._MODES:
             raise ValueError(f'Invalid quantization mode: "{mode}"')
-        if mode == "noise":  # training-time path, not part of the inference hot path
+        if mode == "noise":
             return inputs + torch.empty_like(inputs).uniform_(-0.5, 0.5)
-        outputs = inputs.clone()
-        if means is not None:
-            outputs -= means
-        outputs = torch.round(outputs)
-        if mode == "dequantize":
-            if means is not None:
-                outputs += means
-            return outputs
-        return outputs.int()
+        centred = inputs if means is None else inputs - means
+        rounded = torch.round(centred)
+        if mode == "symbols":
+            return rounded.int()
+        return rounded if means is None else rounded + means
+
+    @staticmethod
+    def dequantize(inputs: Tensor, means: Optional[Tensor] = None) -> Tensor:
+        return inputs.float() if means is None else inputs.type_as(means) + means
 
     def _quantize(self, inputs, mode, means=None):
         warnings.warn("_quantize is deprecated. Use quantize instead.")
         return self.quantize(inputs, mode, means)
-
-    @staticmethod
-    def dequantize(inputs: Tensor, means: Optional[Tensor] = None) -> Tensor:
-        if means is not None:
-            outputs = inputs.type_as(means)
-            outputs += means
-        else:
-            outputs = inputs.float()
-        return outputs
 
     @classmethod
     def _dequantize(cls, inputs, means=None):
@@ -122,37 +111,28 @@ class EntropyModel(nn.Module):
 
     # -- tables ---------------------------------------------------------------------------------------
     def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
-        """entropy_models.py:172-180."""
-        cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32, device=pmf.device)
-        for i, p in enumerate(pmf):
-            prob = torch.cat((p[: pmf_length[i]], tail_mass[i]), dim=0)
-            _cdf = pmf_to_quantized_cdf(prob, self.entropy_coder_precision)
-            cdf[i, : _cdf.size(0)] = _cdf
-        return cdf
+        """API of the reference (entropy_models.py:172-180); the work is tables.quantise_rows."""
+        rows = _tables.quantise_rows(pmf, tail_mass, pmf_length, self.entropy_coder_precision, pmf_to_quantized_cdf)
+        assert rows.shape[1] == max_length + 2
+        return rows
 
-    def _check_cdf_size(self):
-        if self._quantized_cdf.numel() == 0:
-            raise ValueError("Uninitialized CDFs. Run update() first")
-        if len(self._quantized_cdf.size()) != 2:
-            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
+    def _require_tables(self):
+        """The three table buffers must be filled and well-formed before coding (the reference's _check_cdf_size /
+        _check_cdf_length / _check_offsets_size, same messages: they are part of the error contract)."""
+        spec = ((self._quantized_cdf, 2, "Uninitialized CDFs. Run update() first", "Invalid CDF size"),
+                (self._cdf_length, 1, "Uninitialized CDF lengths. Run update() first", "Invalid offsets size"),
+                (self._offset, 1, "Uninitialized offsets. Run update() first", "Invalid offsets size"))
+        for buf, rank, empty_msg, shape_msg in spec:
+            if buf.numel() == 0:
+                raise ValueError(empty_msg)
+            if buf.dim() != rank:
+                raise ValueError(f"{shape_msg} {buf.size()}")
 
-    def _check_offsets_size(self):
-        if self._offset.numel() == 0:
-            raise ValueError("Uninitialized offsets. Run update() first")
-        if len(self._offset.size()) != 1:
-            raise ValueError(f"Invalid offsets size {self._offset.size()}")
-
-    def _check_cdf_length(self):
-        if self._cdf_length.numel() == 0:
-            raise ValueError("Uninitialized CDF lengths. Run update() first")
-        if len(self._cdf_length.size()) != 1:
-            raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
+    _check_cdf_size = _check_cdf_length = _check_offsets_size = _require_tables
 
     def device_tables(self, device) -> _ans.CdfTables:
         """CDF tables resident on `device` (cached until update()/load_state_dict replaces the buffers)."""
-        self._check_cdf_size()
-        self._check_cdf_length()
-        self._check_offsets_size()
+        self._require_tables()
         key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version, str(device))
         if self._tables_cache is None or self._tables_cache[0] != key:
             self._tables_cache = (key, _ans.CdfTables(self._quantized_cdf, self._cdf_length.reshape(-1),
@@ -207,26 +187,30 @@ class EntropyBottleneck(EntropyModel):
         self.filters = tuple(int(f) for f in filters)
         self.init_scale = float(init_scale)
         self.tail_mass = float(tail_mass)
-        filters = (1,) + self.filters + (1,)
-        scale = self.init_scale ** (1 / (len(self.filters) + 1))
-        channels = self.channels
-        for i in range(len(self.filters) + 1):
-            init = np.log(np.expm1(1 / scale / filters[i + 1]))
-            matrix = torch.Tensor(channels, filters[i + 1], filters[i])
-            matrix.data.fill_(init)
-            self.register_parameter(f"_matrix{i:d}", nn.Parameter(matrix))
-            bias = torch.Tensor(channels, filters[i + 1], 1)
-            nn.init.uniform_(bias, -0.5, 0.5)
-            self.register_parameter(f"_bias{i:d}", nn.Parameter(bias))
-            if i < len(self.filters):
-                factor = torch.Tensor(channels, filters[i + 1], 1)
-                nn.init.zeros_(factor)
-                self.register_parameter(f"_factor{i:d}", nn.Parameter(factor))
-        self.quantiles = nn.Parameter(torch.Tensor(channels, 1, 3))
-        init = torch.Tensor([-self.init_scale, 0, self.init_scale])
-        self.quantiles.data = init.repeat(self.quantiles.size(0), 1, 1)
-        target = np.log(2 / self.tail_mass - 1)
-        self.register_buffer("target", torch.Tensor([-target, 0, target]))
+        # Parameters of the per-channel cumulative network (names, shapes and initial values are the state-dict
+        # contract, entropy_models.py:316-348): layer i maps widths[i] -> widths[i + 1] features.
+        widths = (1,) + self.filters + (1,)
+        n_layers = len(widths) - 1
+        per_layer = self.init_scale ** (1.0 / n_layers)
+        C = self.channels
+
+        def fresh(*shape, fill=None, uniform=None):
+            t = torch.Tensor(*shape)
+            if fill is not None:
+                t.data.fill_(fill)
+            elif uniform is not None:
+                nn.init.uniform_(t, -uniform, uniform)
+            return nn.Parameter(t)
+
+        for i in range(n_layers):
+            fan_out, fan_in = widths[i + 1], widths[i]
+            self.register_parameter(f"_matrix{i:d}", fresh(C, fan_out, fan_in, fill=np.log(np.expm1(1 / per_layer / fan_out))))
+            self.register_parameter(f"_bias{i:d}", fresh(C, fan_out, 1, uniform=0.5))
+            if i < n_layers - 1:
+                self.register_parameter(f"_factor{i:d}", fresh(C, fan_out, 1, fill=0.0))
+        self.quantiles = nn.Parameter(torch.Tensor([-self.init_scale, 0, self.init_scale]).repeat(C, 1, 1))
+        logit_tail = np.log(2 / self.tail_mass - 1)
+        self.register_buffer("target", torch.Tensor([-logit_tail, 0, logit_tail]))
         self._lik_params_cache = None
 
     def _get_medians(self) -> Tensor:
@@ -237,23 +221,9 @@ class EntropyBottleneck(EntropyModel):
         if self._offset.numel() > 0 and not force:
             return False
         with torch.no_grad():
-            medians = self.quantiles[:, 0, 1]
-            minima = torch.clamp(torch.ceil(medians - self.quantiles[:, 0, 0]).int(), min=0)
-            maxima = torch.clamp(torch.ceil(self.quantiles[:, 0, 2] - medians).int(), min=0)
-            self._offset = -minima
-            pmf_start = medians - minima
-            pmf_length = maxima + minima + 1
-            max_length = pmf_length.max().item()
-            samples = torch.arange(max_length, device=pmf_start.device)
-            samples = samples[None, :] + pmf_start[:, None, None]
-            lower = self._logits_cumulative(samples - 0.5, stop_gradient=True)
-            upper = self._logits_cumulative(samples + 0.5, stop_gradient=True)
-            sign = -torch.sign(lower + upper)
-            pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
-            pmf = pmf[:, 0, :]
-            tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
-            self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
-            self._cdf_length = pmf_length + 2
+            t = _tables.bottleneck_tables(self.quantiles, lambda v: self._logits_cumulative(v, stop_gradient=True),
+                                          self.entropy_coder_precision, pmf_to_quantized_cdf)
+        self._quantized_cdf, self._cdf_length, self._offset = t.cdf, t.length, t.offset
         self._tables_cache = None
         return True
 
@@ -357,12 +327,7 @@ class GaussianConditional(EntropyModel):
     def __init__(self, scale_table: Optional[Union[List, Tuple]], *args: Any, scale_bound: float = 0.11,
                  tail_mass: float = 1e-9, **kwargs: Any):
         super().__init__(*args, **kwargs)
-        if not isinstance(scale_table, (type(None), list, tuple)):
-            raise ValueError(f'Invalid type for scale_table "{type(scale_table)}"')
-        if isinstance(scale_table, (list, tuple)) and len(scale_table) < 1:
-            raise ValueError(f'Invalid scale_table length "{len(scale_table)}"')
-        if scale_table and (scale_table != sorted(scale_table) or any(s <= 0 for s in scale_table)):
-            raise ValueError(f'Invalid scale_table "({scale_table})"')
+        self._validate_scale_table(scale_table)  # error contract of entropy_models.py:541-552
         self.tail_mass = float(tail_mass)
         if scale_bound is None and scale_table:
             scale_bound = self.scale_table[0]
@@ -371,6 +336,17 @@ class GaussianConditional(EntropyModel):
         self.lower_bound_scale = LowerBound(scale_bound)
         self.register_buffer("scale_table", self._prepare_scale_table(scale_table) if scale_table else torch.Tensor())
         self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]) if scale_bound is not None else None)
+
+    @staticmethod
+    def _validate_scale_table(table) -> None:
+        if table is None:
+            return
+        if not isinstance(table, (list, tuple)):
+            raise ValueError(f'Invalid type for scale_table "{type(table)}"')
+        if len(table) < 1:
+            raise ValueError(f'Invalid scale_table length "{len(table)}"')
+        if any(s <= 0 for s in table) or any(b < a for a, b in zip(table, table[1:])):
+            raise ValueError(f'Invalid scale_table "({table})"')
 
     @staticmethod
     def _prepare_scale_table(scale_table):
@@ -396,20 +372,9 @@ class GaussianConditional(EntropyModel):
     def update(self):
         """entropy_models.py:599-624 (host set-up)."""
         with torch.no_grad():
-            multiplier = -self._standardized_quantile(self.tail_mass / 2)
-            pmf_center = torch.ceil(self.scale_table * multiplier).int()
-            pmf_length = 2 * pmf_center + 1
-            max_length = torch.max(pmf_length).item()
-            device = pmf_center.device
-            samples = torch.abs(torch.arange(max_length, device=device).int() - pmf_center[:, None]).float()
-            samples_scale = self.scale_table.unsqueeze(1).float()
-            upper = self._standardized_cumulative((0.5 - samples) / samples_scale)
-            lower = self._standardized_cumulative((-0.5 - samples) / samples_scale)
-            pmf = upper - lower
-            tail_mass = 2 * lower[:, :1]
-            self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
-            self._offset = -pmf_center
-            self._cdf_length = pmf_length + 2
+            t = _tables.gaussian_tables(self.scale_table, self.tail_mass, self._standardized_cumulative,
+                                        self.entropy_coder_precision, pmf_to_quantized_cdf)
+        self._quantized_cdf, self._cdf_length, self._offset = t.cdf, t.length, t.offset
         self._tables_cache = None
 
     def _flat_call(self, inputs: Optional[Tensor], scales: Tensor, means: Optional[Tensor], want):

@@ -302,15 +302,13 @@ def test_tc_merged_image_layer(hw, batch):
     _close(E.deconv_image(pc, _nhwc(x), L.EPI_CLAMP01).cpu(), ref.clamp(0, 1))
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
-def test_tc_two_cta_variants_match_torch(mode, monkeypatch):
-    """The 10-warp two-CTAs-per-SM kernel variant (PCODEC_TC_SMALL picks where it is used; default = 1-tap short
-    reductions with cout <= 128) against torch, for the tile shapes each mode produces."""
+def test_tc_two_cta_variant_matches_torch():
+    """The 10-warp two-CTAs-per-SM variant of the 3xTF32 kernel (1-tap short reductions with cout <= 128) and its
+    neighbours against torch.  (The PCODEC_TC_SMALL tiling knob only exists in PCODEC_EXPERIMENTS builds.)"""
     from progressivecodec_b200.engine import pack_conv2d
 
-    monkeypatch.setenv("PCODEC_TC_SMALL", mode)
-    E = _engine()
-    torch.manual_seed(int(mode))
+    E = _engine(2)
+    torch.manual_seed(0)
     for cin, cout, k, hw in ((192, 96, 1, (24, 40)), (96, 192, 1, (24, 40)), (128, 64, 3, (16, 24)), (64, 32, 3, (16, 24)),
                              (640, 320, 1, (8, 12))):
         m = nn.Conv2d(cin, cout, k, 1, k // 2)

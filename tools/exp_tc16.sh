@@ -3,7 +3,7 @@
 #   tools/exp_tc16.sh decomp | trace
 cd "$(dirname "$0")/.."
 cp progressivecodec_b200/libpcodec_b200.so /tmp/lib_release.so
-touch progressivecodec_b200/csrc/conv_tc16.cu
+touch progressivecodec_b200/csrc/common.cuh
 PCODEC_EXPERIMENTS=1 bash progressivecodec_b200/csrc/build.sh > /tmp/build_exp.log 2>&1 || { tail /tmp/build_exp.log; echo build failed; exit 1; }
 if [ "${1:-decomp}" = "trace" ]; then
   python tools/trace_tc16.py
@@ -14,4 +14,4 @@ else
   done
 fi
 cp /tmp/lib_release.so progressivecodec_b200/libpcodec_b200.so
-touch progressivecodec_b200/csrc/conv_tc16.cu
+touch progressivecodec_b200/csrc/common.cuh
