@@ -316,7 +316,13 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     }
 
     // =============================== epilogue ===============================
+    // Every lane polls the barrier in its own (inline-asm) loop, so lanes may leave it in different iterations and the
+    // warp is NOT guaranteed to be converged afterwards — but everything below is .sync.aligned (tcgen05.ld), which
+    // requires the whole warp to execute it together.  Re-converge explicitly.  (Without this the kernel ran correctly
+    // almost always and faulted once in a few thousand launches, depending on timing: the intermittent device fault
+    // of round 1.)
     mbar_wait(tmem_full, 0);
+    __syncwarp();
     tc_fence_after();
     if (threadIdx.x == 0) TC_TRACE_G(2);
     const int quarter = warp & 3;      // a warp may only touch TMEM lanes 32*(warp%4) .. +31
@@ -416,6 +422,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
         };
         const float4 z4_ = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 ra0 = NG == 2 ? load_res1(0) : z4_, ra1 = NG == 2 ? load_res1(1) : z4_;  // (NG == 1: no registers to spare)
+        __syncwarp();  // the predicated residual loads above may have split the warp; the TMEM loads are .sync.aligned
         float acc[16];
         if (NG != 2) {  // (96-register variants)
           tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective
@@ -485,6 +492,7 @@ conv_taps_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ 
     } else {
       for (int c0 = third * 16; c0 < bn; c0 += 16 * (TC_PRODUCER_WARPS / 4)) {
         if (n0 + c0 >= d.cout) break;  // padded last N tile
+        __syncwarp();  // lanes that skipped the stores of the previous round (`continue`) rejoin before the collective load
         float acc[16];
         tmem_ld16(lane_addr + (uint32_t)c0, acc);  // warp-collective: executed by all lanes, stores are predicated
         for (int a = 1; a < n_acc; ++a) {

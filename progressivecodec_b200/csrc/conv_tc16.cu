@@ -374,7 +374,13 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
     const bool square_planes = (d.flags & PCODEC_FLAG_SQUARE_OUT_PLANES) != 0;
     const float out_scale = __ldg(P.w_scale + 1) * ((d.flags & PCODEC_FLAG_SQUARE_INPUT) ? 256.0f : 1.0f);
 
+    // Every lane polls the barrier in its own (inline-asm) loop, so lanes may leave it in different iterations and the
+    // warp is NOT guaranteed to be converged afterwards — but everything below is .sync.aligned (tcgen05.ld), which
+    // requires the whole warp to execute it together.  Re-converge explicitly.  (Without this the kernel ran correctly
+    // almost always and faulted once in a few thousand launches, depending on timing: the intermittent device fault
+    // of round 1.)
     mbar_wait(tmem_full, 0);
+    __syncwarp();
     tc_fence_after();
     if (warp == 2) T16(4);
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
@@ -518,6 +524,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       // pixel shuffle: 4 consecutive conv channels = the 2x2 sub-pixels of one output channel (subpel_conv3x3)
       for (int c0 = half * 16; c0 < bn; c0 += 32) {
         if (n0 + c0 >= d.cout) break;
+        __syncwarp();  // lanes that skipped the stores of the previous round (`continue`) rejoin before the collective load
         float acc[16];
         load_acc(c0, acc);  // warp-collective
         if (!row_ok) continue;
