@@ -228,7 +228,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       int seg = 0, tap = 0, kc = 0, seg_cbase = 0, st = 0;
       uint32_t ph = 1;
       for (int s = 0; s < n_steps; ++s) {
-        if (P.debug & 512) mbar_wait(empty(st), ph); else mbar_wait_spin(empty(st), ph);
+        mbar_wait(empty(st), ph);
         const int c = kc * KS;
         const int x = w0 * d.in_step + d.dx[tap], y = h0 * d.in_step + d.dy[tap];
         const int k = tap * d.cin_total + seg_cbase + c;
@@ -274,7 +274,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       for (int s = 0; s < n_steps; ++s) {
         const int sc = d.seg[seg].channels;
         const int ksteps = (min(KS, sc - kc * KS) + 15) >> 4;  // K steps of 16 channels that hold data (the rest is zero fill)
-        if (P.debug & 512) mbar_wait(full(st), ph); else mbar_wait_spin(full(st), ph);
+        mbar_wait(full(st), ph);
         tc_fence_after();
 #ifdef PCODEC_EXPERIMENTS
         if (s == 0) T16(2);
@@ -867,7 +867,6 @@ int pcodec_conv_taps_tc16(const pcodec_conv_desc *desc, void *stream) {
   P.n_ksteps = pl->n_ksteps;
   P.ts = pl->ts;
   P.debug = 0;
-  if (pcodec_knob("PCODEC_TC16_SLEEPWAIT")) P.debug |= 512;  // (A/B knob: suspending try_wait in the producer / issuer threads)
   if (const char *e = pcodec_knob("PCODEC_TC16_DEBUG")) P.debug = atoi(e);
   if (getenv("PCODEC_TC_VERBOSE"))
     fprintf(stderr, "[conv_tc16] grid %dx%d tile %dx%d bn=%d n_tiles=%d n_steps=%d stages=%d n_hi=%d n_lo=%d smem=%d\n", desc->grid_h,

@@ -33,18 +33,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity), "r"(0x989680)
       : "memory");
 }
-// Busy-poll variant for the single producer / issuer threads of a pipeline: mbarrier.test_wait never suspends the thread,
-// so the reaction to a completed phase is a few cycles instead of a wake-up.
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "SPIN_LOOP:\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@!P1 bra SPIN_LOOP;\n\t"
-      "}" ::"r"(bar), "r"(parity)
-      : "memory");
-}
 // exact m / d for m < 2^31 with magic = ceil(2^(31+shift) / d), shift = ceil(log2 d)  (Granlund-Montgomery, N = 31):
 // the tile's pixel coordinates cost 2 multiplies per row instead of 2 integer divisions (~40 instructions each), which
 // was ~2 us of every tile's prologue
