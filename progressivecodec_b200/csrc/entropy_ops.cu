@@ -493,12 +493,14 @@ extern "C" int pcodec_quantile_threshold(const float *scale, int batch, int64_t 
   if (n >= (1ll << 31)) return PCODEC_ERR_UNSUPPORTED;
   constexpr int kKeyCacheMax = 200 * 1024;  // bytes of dynamic shared memory for the key cache
   const int cache = n * 4 <= kKeyCacheMax ? 1 : 0;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(quantile_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKeyCacheMax);
-  });
-  if (attr_err != cudaSuccess) return -(int)attr_err;
+  {  // opt-in to the large dynamic shared memory once per DEVICE (the attribute applies to the current device only)
+    static std::atomic<uint64_t> attr_mask{0};
+    uint64_t bit;
+    if (pcodec_device_needs(attr_mask, &bit)) {
+      PCODEC_CHECK_CUDA(cudaFuncSetAttribute(quantile_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKeyCacheMax));
+      attr_mask.fetch_or(bit, std::memory_order_release);
+    }
+  }
   quantile_threshold_kernel<<<batch, 1024, cache ? (size_t)n * 4 : 0, as_stream(stream)>>>(scale, hw, channels,
                                                                                             pixel_stride, q, thr, cache);
   PCODEC_RETURN_LAUNCH();

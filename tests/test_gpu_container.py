@@ -143,3 +143,26 @@ def test_config4_clic_size_single_encode_all_prefixes():
     assert all(b >= a for a, b in zip(sizes, sizes[1:]))
     assert sizes[-1] == len(blob)
     assert np.isfinite(psnrs).all()
+
+
+def test_arbitrary_levels_round_trip_through_the_f32_header():
+    """Levels that are not exactly representable in the header's f32 fields (0.3, 1.7, 4.2, 7.77): the encoder rounds
+    them to f32 before deriving the mask quantiles, so encoder and decoder compute bit-identical thresholds and every
+    prefix still equals the per-quality round trip at the level the header reports."""
+    import struct
+
+    from progressivecodec_b200 import container as C
+
+    net, _ = build_pair("allscalable", "cuda")
+    x = synthetic_image((1, 3, 128, 192), seed=33)
+    levels = (0.3, 1.7, 4.2, 7.77)
+    blobs = C.encode_progressive(net, x.cuda(), levels)
+    hdr = C.Header.parse(blobs[0])
+    f32 = [struct.unpack("<f", struct.pack("<f", v))[0] for v in levels]
+    assert hdr.levels == f32
+    for k in range(1, len(levels) + 1):
+        out = C.decode_progressive(net, [C.truncate(blobs[0], k)])
+        q = hdr.levels[k - 1]
+        c = net.compress(x.cuda(), quality=q)
+        ref = net.decompress(c["strings"], c["shape"], quality=q)["x_hat"]
+        assert out["n_layers"] == k and torch.equal(out["x_hat"], ref), (k, q)
