@@ -29,12 +29,12 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
     on_result(q, compressed, decompressed) is called on a worker thread after each level (its stream is
     synchronised at that point).  decode_workers: decompress() calls of different levels are independent too, so small
     batches (whose 16-phase decode chain leaves the GPU almost idle) run several of them concurrently; default
-    max(1, min(4, 8 // batch)).  x_for_level(q), when given, is called on the encoder stream before each level and
+    max(1, min(6, 8 // batch)).  x_for_level(q), when given, is called on the encoder stream before each level and
     returns that level's input (e.g. a fresh host->device upload); `x` then only fixes the device and batch size."""
     dev = x.device
     caller_stream = torch.cuda.current_stream(dev)
-    n_workers = decode_workers if decode_workers else max(1, min(4, 8 // max(1, x.shape[0])))
-    n_workers = max(1, min(4, n_workers))  # decompress() reserves 8 engine slots per worker
+    n_workers = decode_workers if decode_workers else max(1, min(6, 8 // max(1, x.shape[0])))
+    n_workers = max(1, min(8, n_workers))  # decompress() reserves 8 engine slots per worker (slots 8w+1 .. 8w+7)
     # One encoder stream and one stream per decode worker, created once per (model, device) and reused by every sweep:
     # torch hands out streams round-robin from a pool of 32, and every new stream gets its own caching-allocator pool,
     # so per-sweep streams grew the footprint by ~1.5 GB per sweep until the pool wrapped around.
