@@ -35,10 +35,10 @@ records = []
 orig = eng.Engine.conv
 
 
-def timed(self, pc, segs, out, epi=0, r1=None, r2=None, flags=0, fmt=3):
+def timed(self, pc, segs, out, epi=0, r1=None, r2=None, flags=0, fmt=3, square_planes=False):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()  # (includes the split-plane conversions this launch triggers for inputs no epilogue produced)
-    r = orig(self, pc, segs, out, epi, r1, r2, flags, fmt)
+    r = orig(self, pc, segs, out, epi, r1, r2, flags, fmt, square_planes)
     e1.record()
     a0 = segs[0]
     if pc.out_step == 1:
