@@ -34,8 +34,10 @@ namespace {
 constexpr int BM = 128;                // output pixels per tile (TMEM lanes)
 constexpr int KS = 64;                 // fp16 channels per K slab = 128 bytes = one swizzle row
 constexpr int A_BYTES = BM * 128;      // one plane of one A tile
-constexpr int NWARPS = 10;             // 0: TMA producer, 1: TMEM alloc + MMA issuer, 2..9: epilogue (two per lane quarter)
-constexpr int EPI_WARPS = 8;
+// warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2..: epilogue.  Two instantiations: EW = 8 epilogue warps
+// (10 warps, <= 102 registers: two CTAs per SM for the short tiles) and EW = 12 (14 warps, one CTA per SM: a third warp
+// per TMEM lane quarter shortens the un-overlapped epilogue of the 512-column tiles).
+constexpr int EPI_WARPS_MAX = 12;
 constexpr int SMEM_LIMIT = 225 * 1024;
 constexpr int SMEM_HALF = 113 * 1024;  // two resident CTAs (tiles of <= 256 TMEM columns): 2 x (113 KB + 1 KB reserved) <= 228 KB
 constexpr uint32_t PLAN_MAGIC = 0x31366370u;
@@ -153,8 +155,10 @@ __device__ long long g_trace16[128];
 #define T16(ev) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(32 * NWARPS, 2)
+template <int EW>
+__global__ void __launch_bounds__(32 * (EW + 2), EW == 8 ? 2 : 1)
 conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
+  constexpr int EPI_WARPS = EW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const pcodec_conv_desc &d = P.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -331,7 +335,8 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
     // =============================== epilogue warps ===============================
     const int ew = warp - 2;            // 0..7
     const int quarter = warp & 3;       // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    const int half = ew >> 2;           // the two warps of a quarter interleave the 16-column groups
+    const int half = ew >> 2;           // the EW/4 warps of a quarter interleave the 16-column groups
+    constexpr int CSTEP = 16 * (EW / 4);  // columns between two groups of the same warp
     const int row = quarter * 32 + lane;
     const int ti = row >> P.tw_shift, tj = row & (P.tw - 1);
     const int gh = h0 + ti, gw = w0 + tj;
@@ -346,11 +351,11 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
     const bool r1p = !d.r1 && d.r1_16.hi, r2p = !d.r2 && d.r2_16.hi;  // residuals given as split planes
     if ((d.r1 || d.r2 || r1p || r2p) && !shuffle && row_ok) {
       // residual values do not depend on the accumulators: pull them into L2 while the main loop runs
-      for (int c = half * 32; c < bn && n0 + c < d.cout; c += 64) {
+      for (int c = half * 32; c < bn && n0 + c < d.cout; c += 32 * (EW / 4)) {
         if (d.r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r1 + opix * d.r1_pixel_stride + n0 + c));
         if (d.r2) asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r2 + opix * d.r2_pixel_stride + n0 + c));
       }
-      for (int c = half * 64; c < bn && n0 + c < d.cout; c += 128) {
+      for (int c = half * 64; c < bn && n0 + c < d.cout; c += 64 * (EW / 4)) {
         if (r1p) {
           asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r1_16.hi + opix * d.r1_16.pixel_stride + n0 + c));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(d.r1_16.lo + opix * d.r1_16.pixel_stride + n0 + c));
@@ -465,7 +470,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
         ok_t |= (__shfl_sync(0xFFFFFFFFu, row_ok ? 1u : 0u, src) & 1u) << i;
       }
       const uint32_t wr_off = (uint32_t)lane * 64u, wr_x = (uint32_t)(lane >> 1) & 3u;
-      for (int c0 = half * 16; c0 < bn; c0 += 32) {
+      for (int c0 = half * 16; c0 < bn; c0 += CSTEP) {
         if (n0 + c0 >= d.cout) break;  // padded last N tile
         const int co = n0 + c0 + 4 * cc;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -522,7 +527,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       }
     } else {
       // pixel shuffle: 4 consecutive conv channels = the 2x2 sub-pixels of one output channel (subpel_conv3x3)
-      for (int c0 = half * 16; c0 < bn; c0 += 32) {
+      for (int c0 = half * 16; c0 < bn; c0 += CSTEP) {
         if (n0 + c0 >= d.cout) break;
         __syncwarp();  // lanes that skipped the stores of the previous round (`continue`) rejoin before the collective load
         float acc[16];
@@ -794,7 +799,7 @@ extern "C" int pcodec_conv_plan(pcodec_conv_desc *desc) {
   if (pl->bn == 0) return PCODEC_ERR_UNSUPPORTED;
   pl->n_tiles = (desc->cout + pl->bn - 1) / pl->bn;
   const int stage_bytes = 2 * A_BYTES + 2 * pl->bn * 128;
-  auto need = [&](int st) { return std::max(st * stage_bytes, EPI_WARPS * 2048) + 8 * (2 * st + 2) + 64; };
+  auto need = [&](int st) { return std::max(st * stage_bytes, EPI_WARPS_MAX * 2048) + 8 * (2 * st + 2) + 64; };
   int tmem_cols = 32;
   while (tmem_cols < (pl->n_hi + pl->n_lo) * pl->bn + (pl->ts ? 64 : 0)) tmem_cols <<= 1;
   // tiles of <= 256 TMEM columns: keep the footprint small enough for TWO resident CTAs (one's prologue / epilogue
@@ -875,13 +880,19 @@ int pcodec_conv_taps_tc16(const pcodec_conv_desc *desc, void *stream) {
     static std::atomic<uint64_t> attr_mask{0};
     uint64_t bit;
     if (pcodec_device_needs(attr_mask, &bit)) {
-      PCODEC_CHECK_CUDA(cudaFuncSetAttribute(conv_taps_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      PCODEC_CHECK_CUDA(cudaFuncSetAttribute(conv_taps_tc16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      PCODEC_CHECK_CUDA(cudaFuncSetAttribute(conv_taps_tc16_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
       attr_mask.fetch_or(bit, std::memory_order_release);
     }
   }
   const int64_t n_ctas = (int64_t)pl->tiles_w * pl->tiles_h * desc->batch * pl->n_tiles;
   if (n_ctas >= (1ll << 31)) return PCODEC_ERR_UNSUPPORTED;
   dim3 grid((unsigned)n_ctas);
-  conv_taps_tc16_kernel<<<grid, 32 * NWARPS, pl->smem, as_stream(stream)>>>(P);
+  // tiles that own the SM (more than 113 KB / 256 TMEM columns) get the 12-epilogue-warp instantiation
+  static const bool wide_epi = [] { const char *e = pcodec_knob("PCODEC_TC16_EPI12"); return !e || atoi(e) != 0; }();
+  if (wide_epi && pl->smem > SMEM_HALF)
+    conv_taps_tc16_kernel<12><<<grid, 32 * 14, pl->smem, as_stream(stream)>>>(P);
+  else
+    conv_taps_tc16_kernel<8><<<grid, 32 * 10, pl->smem, as_stream(stream)>>>(P);
   PCODEC_RETURN_LAUNCH();
 }
