@@ -683,9 +683,12 @@ class ChannelProgresssiveWACNN(nn.Module):
 
     @torch.no_grad()
     def compress(self, x, quality=0.0, mask_pol=None, cust_map=None, return_device_streams: bool = False,
-                 debug: Optional[dict] = None, _rem=None, _rem_ckpt=None, _no_entropy: bool = False):
+                 debug: Optional[dict] = None, _rem=None, _rem_ckpt=None, _no_entropy: bool = False,
+                 _planes_only: bool = False):
         """CHProg_cnn.py:686-847.  One batched rANS launch codes every (slice, image) stream.
-        `debug` (tests only) receives the device symbol / index planes [n_slices, B, 32*h*w] and z symbols."""
+        `debug` (tests only) receives the device symbol / index planes [n_slices, B, 32*h*w] and z symbols.
+        `_planes_only` (graphs.py) stops before the entropy coder and returns the symbol / index planes: everything up to
+        there is free of host synchronisation and can be captured in a CUDA graph; `_entropy_tail` finishes the call."""
         mask_pol = self.mask_policy if mask_pol is None else mask_pol
         x = self._check_input(x)
         P = self.prepare()
@@ -725,10 +728,20 @@ class ChannelProgresssiveWACNN(nn.Module):
             debug.update(symbols=sym, indexes=idx, z_symbols=z_sym, y=E.to_nchw(y), y_hat_base=E.to_nchw(y_hat_base))
         if _no_entropy:  # REM real_compress=False (CHProgREM.py:857-860): quantise only; y_hat is what a round trip gives
             return {"strings": None, "shape": torch.Size([z.H, z.W]), "masks": masks, "y_hat": E.to_nchw(y_hat_out)}
-        z_data, z_off = _ans.encode_batch(z_sym, z_idx, P["eb_tables"])
-        y_data, y_off = _ans.encode_batch(sym.reshape(n_slices * B, n), idx.reshape(n_slices * B, n), P["gc_tables"])
-        shape = torch.Size([z.H, z.W])
         extra = {"y_hat": E.to_nchw(y_hat_out)} if _rem is not None else {}
+        planes = {"sym": sym, "idx": idx, "z_sym": z_sym, "z_idx": z_idx, "masks": masks,
+                  "shape": torch.Size([z.H, z.W]), "extra": extra}
+        if _planes_only:
+            return planes
+        return self._entropy_tail(planes, return_device_streams)
+
+    def _entropy_tail(self, planes: dict, return_device_streams: bool):
+        """Entropy-code the planes of a compress() call (one host synchronisation per table set: the stream lengths)."""
+        P = self.prepare()
+        sym, idx, masks, shape, extra = planes["sym"], planes["idx"], planes["masks"], planes["shape"], planes["extra"]
+        n_slices, B, n = sym.shape
+        z_data, z_off = _ans.encode_batch(planes["z_sym"], planes["z_idx"], P["eb_tables"])
+        y_data, y_off = _ans.encode_batch(sym.reshape(n_slices * B, n), idx.reshape(n_slices * B, n), P["gc_tables"])
         if return_device_streams:
             return {"streams": (y_data, y_off, z_data, z_off), "shape": shape, "masks": masks, "batch": B, **extra}
         flat = _ans.split_streams(y_data, y_off)

@@ -21,7 +21,8 @@ _streams_lock = threading.Lock()
 def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[str] = None, host_strings: bool = False,
           on_result: Optional[Callable[[float, dict, dict], None]] = None, keep: bool = True,
           decode_workers: Optional[int] = None,
-          x_for_level: Optional[Callable[[float], torch.Tensor]] = None) -> List[Optional[torch.Tensor]]:
+          x_for_level: Optional[Callable[[float], torch.Tensor]] = None,
+          graphs: Optional[bool] = None) -> List[Optional[torch.Tensor]]:
     """compress + decompress `x` at every level of `qualities`; returns the reconstructions (``x_hat`` per level).
 
     host_strings=False keeps the rANS streams on the device between the two stages (compress(...,
@@ -30,7 +31,10 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
     synchronised at that point).  decode_workers: decompress() calls of different levels are independent too, so small
     batches (whose 16-phase decode chain leaves the GPU almost idle) run several of them concurrently; default
     max(1, min(6, 8 // batch)).  x_for_level(q), when given, is called on the encoder stream before each level and
-    returns that level's input (e.g. a fresh host->device upload); `x` then only fixes the device and batch size."""
+    returns that level's input (e.g. a fresh host->device upload); `x` then only fixes the device and batch size.
+    graphs: replay the launch-bound network parts of both stages as CUDA graphs (graphs.py; default: batches of <= 2
+    images, where the host — not the GPU — bounds the sweep).  The `masks` of a graphed compress() and the reconstructions
+    handed to on_result alias static graph buffers: they are valid until the same level is coded again."""
     dev = x.device
     caller_stream = torch.cuda.current_stream(dev)
     n_workers = decode_workers if decode_workers else max(1, min(6, 8 // max(1, x.shape[0])))
@@ -50,32 +54,60 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
     for st in dec_streams:  # work of an earlier sweep's caller (e.g. frees recorded on its stream) is ordered first
         st.wait_stream(caller_stream)
     enc_stream.wait_stream(caller_stream)
+    use_graphs = (x.shape[0] <= 2) if graphs is None else bool(graphs)
+    g_enc, g_dec = {}, {}
+    if use_graphs:
+        # capture (once per model, shape, level and worker) on this thread, before the workers start
+        from . import graphs as _graphs
+
+        gc_ = _graphs.cache(net)
+        B, H, W = x.shape[0], x.shape[2], x.shape[3]
+        zshape, n_per = (H // 64, W // 64), 32 * (H // 16) * (W // 16)
+        for i, q in enumerate(qualities):
+            k_enc = ("enc", dev, tuple(x.shape), float(q), mask_pol)
+            if k_enc not in gc_:
+                gc_[k_enc] = _graphs.GraphedCompress(net, tuple(x.shape), q, mask_pol, enc_stream)
+            g_enc[i] = gc_[k_enc]
+            wk = i % n_workers
+            k_dec = ("dec", dev, zshape, float(q), mask_pol, B, wk)
+            if k_dec not in gc_:
+                gc_[k_dec] = _graphs.GraphedDecompress(net, zshape, q, mask_pol, B, net.ns0 if q <= 0 else net.ns1, n_per,
+                                                       wk, dec_streams[wk])
+            g_dec[i] = gc_[k_dec]
+    # with graphs a level belongs to a fixed worker (its graph lives on that worker's engine slot and stream)
+    queues = [queue.Queue(maxsize=2) for _ in range(n_workers)] if use_graphs else None
     q_items: "queue.Queue" = queue.Queue(maxsize=n_workers + 1)
     outs: List[Optional[torch.Tensor]] = [None] * len(qualities)
     err: List[BaseException] = []
 
     def consumer(k: int):
         dec_stream = dec_streams[k]
+        my_q = queues[k] if use_graphs else q_items
         try:
             with torch.cuda.device(dev), torch.cuda.stream(dec_stream), torch.no_grad():
                 while True:
-                    item = q_items.get()
+                    item = my_q.get()
                     if item is None:
-                        q_items.put(None)  # pass the end marker on to the other workers
+                        if not use_graphs:
+                            q_items.put(None)  # pass the end marker on to the other workers
                         return
                     i, q, c = item
                     src = c["strings"] if host_strings else c
-                    r = net.decompress(src, c["shape"], quality=q, mask_pol=mask_pol, _worker=k)
+                    if use_graphs:
+                        r = {"x_hat": g_dec[i](src)}
+                    else:
+                        r = net.decompress(src, c["shape"], quality=q, mask_pol=mask_pol, _worker=k)
                     dec_stream.synchronize()  # `c` may be released (and its memory reused by the encoder stream) now
                     if on_result is not None:
                         on_result(q, c, r)
                     if keep:
-                        outs[i] = r["x_hat"]
+                        outs[i] = r["x_hat"].clone() if use_graphs else r["x_hat"]
         except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
             err.append(e)
-            while q_items.get() is not None:  # drain so the producer never blocks on a dead consumer
+            while my_q.get() is not None:  # drain so the producer never blocks on a dead consumer
                 pass
-            q_items.put(None)
+            if not use_graphs:
+                q_items.put(None)
 
     workers = [threading.Thread(target=consumer, args=(k,), name=f"pcodec-decompress-{k}") for k in range(n_workers)]
     for t in workers:
@@ -86,11 +118,18 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
                 if err:
                     break
                 xq = x_for_level(q) if x_for_level is not None else x
-                c = net.compress(xq, quality=q, mask_pol=mask_pol, return_device_streams=not host_strings)
+                if use_graphs:
+                    c = g_enc[i](xq, return_device_streams=not host_strings)
+                else:
+                    c = net.compress(xq, quality=q, mask_pol=mask_pol, return_device_streams=not host_strings)
                 enc_stream.synchronize()  # compress() has already synchronised to learn the stream lengths
-                q_items.put((i, q, c))
+                (queues[i % n_workers] if use_graphs else q_items).put((i, q, c))
     finally:
-        q_items.put(None)
+        if use_graphs:
+            for qq in queues:
+                qq.put(None)
+        else:
+            q_items.put(None)
         for t in workers:
             t.join()
     caller_stream.wait_stream(enc_stream)

@@ -450,3 +450,33 @@ def test_headline_shape_images_of_a_pipelined_batch64_vs_oracle():
             assert abs(b_gpu - b_ref) <= 0.005 * b_ref, (q, b, b_gpu, b_ref)
             rec_orc = orc.decompress(o["strings"], tuple(o["shape"]), quality=q)["x_hat"]
             assert abs(psnr(recs[qi][b:b + 1].cpu(), x[b:b + 1]) - psnr(rec_orc, x[b:b + 1])) <= 0.02, (q, b)
+
+
+@pytest.mark.parametrize("batch", [1, 2])
+def test_graphed_small_batch_sweep_equals_sequential_calls(batch):
+    """Small batches replay the launch-bound parts of compress() / decompress() as CUDA graphs (graphs.py): same
+    reconstructions and the same streams as the eager calls, on the capture sweep and on pure replays, through device
+    streams and through python `bytes`."""
+    from progressivecodec_b200 import pipeline
+
+    net, _ = build_pair("authors", "cuda")
+    x = synthetic_image((batch, 3, 128, 192), seed=41).cuda()
+    qs = [0, 0.05, 1.25, 10]
+    seq = []
+    for q in qs:
+        c = net.compress(x, quality=q)
+        seq.append((c["strings"], net.decompress(c["strings"], c["shape"], quality=q)["x_hat"]))
+    for rep in range(3):  # first call captures, the others replay
+        x_in = x if rep < 2 else torch.flip(x, dims=[3]).contiguous()
+        seen = {}
+        got = pipeline.sweep(net, x_in, qs, graphs=True, host_strings=(rep == 1),
+                             on_result=(lambda q, c, r: seen.__setitem__(q, c["strings"])) if rep == 1 else None)
+        if rep < 2:
+            for i, q in enumerate(qs):
+                assert torch.equal(got[i], seq[i][1]), (rep, q)
+                if rep == 1:
+                    assert seen[q][0] == seq[i][0][0] and seen[q][1] == seq[i][0][1]
+        else:  # a different image through the same graphs
+            for i, q in enumerate(qs):
+                c = net.compress(x_in, quality=q)
+                assert torch.equal(got[i], net.decompress(c["strings"], c["shape"], quality=q)["x_hat"]), q
