@@ -24,20 +24,20 @@ from . import ans as _ans
 class GraphedCompress:
     """net.compress(x, quality) for one input shape: graph of the network part + eager entropy-coding tail."""
 
-    def __init__(self, net, x_shape, quality, mask_pol, stream: torch.cuda.Stream):
+    def __init__(self, net, x_shape, quality, mask_pol, stream: torch.cuda.Stream, slot: int = 0):
         dev = net._device()
         self.net, self.quality, self.mask_pol, self.stream = net, quality, mask_pol, stream
         self.x = torch.zeros(x_shape, dtype=torch.float32, device=dev)
         with torch.cuda.stream(stream), torch.no_grad():
             for _ in range(2):  # sizes the arena, builds the launch plans, sets the function attributes
-                net.compress(self.x, quality=quality, mask_pol=mask_pol, _planes_only=True)
+                net.compress(self.x, quality=quality, mask_pol=mask_pol, _planes_only=True, _slot=slot)
             stream.synchronize()
             E = net.prepare()["eng"]
-            self._pin = E._slots[0].arena.buf  # the activations' memory must outlive the graph
+            self._pin = E._slots[slot].arena.buf  # the activations' memory must outlive the graph
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=stream, capture_error_mode="thread_local"):
-                self.planes = net.compress(self.x, quality=quality, mask_pol=mask_pol, _planes_only=True)
-            if E._slots[0].arena.buf is not self._pin:
+                self.planes = net.compress(self.x, quality=quality, mask_pol=mask_pol, _planes_only=True, _slot=slot)
+            if E._slots[slot].arena.buf is not self._pin:
                 raise RuntimeError("arena moved during graph capture")
 
     def __call__(self, x: torch.Tensor, return_device_streams: bool):
@@ -52,6 +52,7 @@ class GraphedDecompress:
     def __init__(self, net, shape, quality, mask_pol, batch: int, n_slices: int, n_per_stream: int, worker: int,
                  stream: torch.cuda.Stream):
         dev = net._device()
+        mask_pol = net.mask_policy if mask_pol is None else mask_pol  # (decompress() resolves the default the same way)
         self.net, self.quality, self.batch, self.n_slices = net, quality, batch, n_slices
         self.shape = torch.Size([int(shape[0]), int(shape[1])])
         Cz = net.entropy_bottleneck._quantized_cdf.size(0)

@@ -562,9 +562,9 @@ class ChannelProgresssiveWACNN(nn.Module):
             raise ValueError("expected [B,3,H,W] with H and W multiples of 64 (pad as training/step.py:317-319 does)")
         return x.contiguous().float()
 
-    def _encoder_front(self, P, x: Tensor, enhanced: bool, want_z_lik: bool):
+    def _encoder_front(self, P, x: Tensor, enhanced: bool, want_z_lik: bool, slot: int = 0):
         E = P["eng"]
-        E.begin(0)
+        E.begin(slot)
         y = self._g_a(P, x)
         z = self._h_a(P, y)
         B, hw_z = z.B, z.H * z.W
@@ -684,7 +684,7 @@ class ChannelProgresssiveWACNN(nn.Module):
     @torch.no_grad()
     def compress(self, x, quality=0.0, mask_pol=None, cust_map=None, return_device_streams: bool = False,
                  debug: Optional[dict] = None, _rem=None, _rem_ckpt=None, _no_entropy: bool = False,
-                 _planes_only: bool = False):
+                 _planes_only: bool = False, _slot: int = 0):
         """CHProg_cnn.py:686-847.  One batched rANS launch codes every (slice, image) stream.
         `debug` (tests only) receives the device symbol / index planes [n_slices, B, 32*h*w] and z symbols.
         `_planes_only` (graphs.py) stops before the entropy coder and returns the symbol / index planes: everything up to
@@ -693,7 +693,9 @@ class ChannelProgresssiveWACNN(nn.Module):
         x = self._check_input(x)
         P = self.prepare()
         E: Engine = P["eng"]
-        y, z, z_sym, z_idx, _zl, lm, ls = self._encoder_front(P, x, enhanced=not (quality == 0), want_z_lik=False)
+        # `_slot` (graphs.py): engine context of this call; concurrent encoder threads use distinct slots
+        y, z, z_sym, z_idx, _zl, lm, ls = self._encoder_front(P, x, enhanced=not (quality == 0), want_z_lik=False,
+                                                              slot=_slot)
         B, h, w = y.B, y.H, y.W
         n = 32 * h * w
         n_slices = self.ns0 if quality <= 0 else self.ns1
