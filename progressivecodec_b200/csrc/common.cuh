@@ -101,4 +101,46 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erf_branchfree(x * 0.70710678118654752440f));
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot for two IEEE round-to-nearest operations).  The conv
+// epilogues are bound by the number of instructions their few warps can issue, and half of those instructions were the
+// 13 FMAs + 5 multiplies / adds of every GELU: evaluating two elements per instruction gives bit-identical results
+// (same operations, same rounding, same order per element) for ~2/3 of the issue slots.
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 f2_pack(float a, float b) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ F2 f2_dup(float a) { return f2_pack(a, a); }
+__device__ __forceinline__ void f2_unpack(F2 p, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 f2_sub(F2 a, F2 b) { F2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+
+// gelu_erf() of two values: the operation sequence of erf_branchfree() / gelu_erf() above, element for element.
+__device__ __forceinline__ void gelu_erf2(float x0, float x1, float &o0, float &o1) {
+  const F2 x = f2_pack(x0, x1);
+  const F2 a = f2_mul(x, f2_dup(0.70710678118654752440f));
+  float a0, a1;
+  f2_unpack(a, a0, a1);
+  const float t0 = fabsf(a0), t1 = fabsf(a1);
+  const F2 t = f2_pack(t0, t1), nt = f2_pack(-t0, -t1), s = f2_mul(a, a);
+  F2 r = f2_fma(f2_dup(-1.72853470e-5f), t, f2_dup(3.83197126e-4f));
+  const F2 u = f2_fma(f2_dup(-3.88396438e-3f), t, f2_dup(2.42546219e-2f));
+  r = f2_fma(r, s, u);
+  r = f2_fma(r, t, f2_dup(-1.06777877e-1f));
+  r = f2_fma(r, t, f2_dup(-6.34846687e-1f));
+  r = f2_fma(r, t, f2_dup(-1.28717512e-1f));
+  r = f2_fma(r, t, nt);
+  float r0, r1;
+  f2_unpack(r, r0, r1);
+  const float big0 = copysignf(1.0f - expf(r0), a0), big1 = copysignf(1.0f - expf(r1), a1);
+  F2 q = f2_fma(f2_dup(-5.96761703e-4f), s, f2_dup(4.99119423e-3f));
+  q = f2_fma(q, s, f2_dup(-2.67681349e-2f));
+  q = f2_fma(q, s, f2_dup(1.12819925e-1f));
+  q = f2_fma(q, s, f2_dup(-3.76125336e-1f));
+  q = f2_fma(q, s, f2_dup(1.28379166e-1f));
+  float s0, s1;
+  f2_unpack(f2_fma(q, a, a), s0, s1);
+  const F2 e = f2_pack(t0 > 0.927734375f ? big0 : s0, t1 > 0.927734375f ? big1 : s1);
+  f2_unpack(f2_mul(f2_mul(f2_dup(0.5f), x), f2_add(f2_dup(1.0f), e)), o0, o1);
+}
+
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -79,7 +79,9 @@ __device__ __forceinline__ float h_hi_f(uint32_t p) { return __half2float(__usho
 // two fp32 -> packed (hi, hi) and (lo, lo) fp16 pairs of the split format
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
   hi = pack_h2(a, b);
-  lo = pack_h2((a - h_lo_f(hi)) * LO_SCALE, (b - h_hi_f(hi)) * LO_SCALE);
+  float l0, l1;  // (a - hi(a)) * 2^11, both operations exact, as one packed subtract and one packed multiply
+  f2_unpack(f2_mul(f2_sub(f2_pack(a, b), f2_pack(h_lo_f(hi), h_hi_f(hi))), f2_dup(LO_SCALE)), l0, l1);
+  lo = pack_h2(l0, l1);
 }
 
 // ---------------------------------------------------------------------------------------------------------

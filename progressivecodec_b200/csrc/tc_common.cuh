@@ -198,9 +198,15 @@ static __device__ __noinline__ float4 tc_epilogue4(int epi, float4 v, float4 r1,
   } while (0)
   float4 o;
   switch (epi) {
-    case PCODEC_EPI_GELU: PC_EACH(gelu_erf(a)); break;
+    case PCODEC_EPI_GELU:
+      gelu_erf2(v.x, v.y, o.x, o.y);
+      gelu_erf2(v.z, v.w, o.z, o.w);
+      break;
     case PCODEC_EPI_ADD: PC_EACH(a + p); break;
-    case PCODEC_EPI_ADD_GELU: PC_EACH(gelu_erf(a + p)); break;
+    case PCODEC_EPI_ADD_GELU:
+      gelu_erf2(v.x + r1.x, v.y + r1.y, o.x, o.y);
+      gelu_erf2(v.z + r1.z, v.w + r1.w, o.z, o.w);
+      break;
     case PCODEC_EPI_GATE: PC_EACH(q * sigmoid_f(a) + p); break;
     case PCODEC_EPI_GDN: PC_EACH(p * rsqrtf(a)); break;
     case PCODEC_EPI_IGDN: PC_EACH(p * sqrtf(a)); break;
@@ -234,9 +240,19 @@ static __device__ __noinline__ F8 tc_epilogue8(int epi, F8 v, F8 r1, F8 r2, bool
   } while (0)
   F8 o;
   switch (epi) {
-    case PCODEC_EPI_GELU: PC_EACH8(gelu_erf(a)); break;
+    case PCODEC_EPI_GELU:
+      gelu_erf2(v.a.x, v.a.y, o.a.x, o.a.y);
+      gelu_erf2(v.a.z, v.a.w, o.a.z, o.a.w);
+      gelu_erf2(v.b.x, v.b.y, o.b.x, o.b.y);
+      gelu_erf2(v.b.z, v.b.w, o.b.z, o.b.w);
+      break;
     case PCODEC_EPI_ADD: PC_EACH8(a + p); break;
-    case PCODEC_EPI_ADD_GELU: PC_EACH8(gelu_erf(a + p)); break;
+    case PCODEC_EPI_ADD_GELU:
+      gelu_erf2(v.a.x + r1.a.x, v.a.y + r1.a.y, o.a.x, o.a.y);
+      gelu_erf2(v.a.z + r1.a.z, v.a.w + r1.a.w, o.a.z, o.a.w);
+      gelu_erf2(v.b.x + r1.b.x, v.b.y + r1.b.y, o.b.x, o.b.y);
+      gelu_erf2(v.b.z + r1.b.z, v.b.w + r1.b.w, o.b.z, o.b.w);
+      break;
     case PCODEC_EPI_GATE: PC_EACH8(q * sigmoid_f(a) + p); break;
     case PCODEC_EPI_GDN: PC_EACH8(p * rsqrtf(a)); break;
     case PCODEC_EPI_IGDN: PC_EACH8(p * sqrtf(a)); break;
