@@ -27,6 +27,7 @@ class GraphedCompress:
     def __init__(self, net, x_shape, quality, mask_pol, stream: torch.cuda.Stream, slot: int = 0):
         dev = net._device()
         self.net, self.quality, self.mask_pol, self.stream = net, quality, mask_pol, stream
+        self._state = net.prepare()  # the weights / tables / arenas the graph points into live as long as the graph
         self.x = torch.zeros(x_shape, dtype=torch.float32, device=dev)
         with torch.cuda.stream(stream), torch.no_grad():
             for _ in range(2):  # sizes the arena, builds the launch plans, sets the function attributes
@@ -41,6 +42,8 @@ class GraphedCompress:
                 raise RuntimeError("arena moved during graph capture")
 
     def __call__(self, x: torch.Tensor, return_device_streams: bool):
+        if self.net.prepare() is not self._state:
+            raise RuntimeError("the model was re-prepared after this graph was captured")
         self.x.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.net._entropy_tail(self.planes, return_device_streams)
@@ -63,7 +66,7 @@ class GraphedDecompress:
         self.y_off = torch.zeros(n_slices * batch + 1, dtype=torch.int64, device=dev)
         self.z_off = torch.zeros(batch + 1, dtype=torch.int64, device=dev)
         self.slot = 1 + 8 * worker
-        P = net.prepare()
+        P = self._state = net.prepare()
         E = P["eng"]
         # warm-up needs DECODABLE input (the decoder of garbage is safe but data dependent in time, not in launches):
         # all-zero offsets decode zero-length streams, which the kernel treats as streams of zero words
@@ -83,6 +86,8 @@ class GraphedDecompress:
     def __call__(self, src) -> torch.Tensor:
         """src: the dict of compress(return_device_streams=True) or the reference-API `strings` list."""
         dev = self.y_data.device
+        if self.net.prepare() is not self._state:
+            raise RuntimeError("the model was re-prepared after this graph was captured")
         if isinstance(src, dict):
             y_data, y_off, z_data, z_off = src["streams"]
         else:
@@ -100,4 +105,8 @@ class GraphedDecompress:
 
 
 def cache(net) -> Dict[Tuple, object]:
-    return net.__dict__.setdefault("_graph_cache", {})
+    """Graphs of the model's CURRENT prepared state.  They are stored inside that state: a graph has the device addresses
+    of the packed weights, the entropy tables and the engine's arenas baked in, and all of those are rebuilt (the old
+    ones freed) whenever the model is re-prepared — after update(), load_state_dict() or any .to() / .cuda() call, even
+    one that moves nothing.  A cache on the model itself outlived them and replayed graphs over freed memory."""
+    return net.prepare().setdefault("_graph_cache", {})

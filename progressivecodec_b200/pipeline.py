@@ -22,7 +22,7 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
           on_result: Optional[Callable[[float, dict, dict], None]] = None, keep: bool = True,
           decode_workers: Optional[int] = None,
           x_for_level: Optional[Callable[[float], torch.Tensor]] = None,
-          graphs: Optional[bool] = None) -> List[Optional[torch.Tensor]]:
+          graphs: Optional[bool] = None, encoders: Optional[int] = None) -> List[Optional[torch.Tensor]]:
     """compress + decompress `x` at every level of `qualities`; returns the reconstructions (``x_hat`` per level).
 
     host_strings=False keeps the rANS streams on the device between the two stages (compress(...,
@@ -32,6 +32,9 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
     batches (whose 16-phase decode chain leaves the GPU almost idle) run several of them concurrently; default
     max(1, min(6, 8 // batch)).  x_for_level(q), when given, is called on the encoder stream before each level and
     returns that level's input (e.g. a fresh host->device upload); `x` then only fixes the device and batch size.
+    With several decode workers the levels are coded in descending quality (the results keep the caller's order): the
+    highest levels carry the most symbols, i.e. the longest serial decode chains, and those should start first instead of
+    finishing the sweep alone.  encoders: concurrent compress() threads of a graphed sweep (default 4).
     graphs: replay the launch-bound network parts of both stages as CUDA graphs (graphs.py; default: batches of <= 2
     images, where the host — not the GPU — bounds the sweep).  The `masks` of a graphed compress() and the reconstructions
     handed to on_result alias static graph buffers: they are valid until the same level is coded again."""
@@ -46,7 +49,11 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
     # torch hands out streams round-robin from a pool of 32, and every new stream gets its own caching-allocator pool,
     # so per-sweep streams grew the footprint by ~1.5 GB per sweep until the pool wrapped around.
     # graphs take the host out of the loop, and one small image leaves most SMs idle: code several levels at once
-    n_enc = max(1, min(3, len(qualities))) if use_graphs else 1
+    n_enc = max(1, min(encoders if encoders else 4, 6, len(qualities))) if use_graphs else 1
+    # processing order: position p of the sweep codes level order[p] (graphs, streams and workers are tied to p)
+    order = list(range(len(qualities)))
+    if n_workers > 1:
+        order.sort(key=lambda i: -float(qualities[i]))
     with _streams_lock:
         cache = net.__dict__.setdefault("_pipeline_streams", {})
         have = cache.setdefault(dev, {"enc": [], "dec": []})
@@ -66,14 +73,15 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
         gc_ = _graphs.cache(net)
         B, H, W = x.shape[0], x.shape[2], x.shape[3]
         zshape, n_per = (H // 64, W // 64), 32 * (H // 16) * (W // 16)
-        for i, q in enumerate(qualities):
-            ek = i % n_enc
+        for p, i in enumerate(order):
+            q = qualities[i]
+            ek = p % n_enc
             k_enc = ("enc", dev, tuple(x.shape), float(q), mask_pol, ek)
             if k_enc not in gc_:  # encoder thread ek: engine slot 0 / 70 + ek, stream enc_streams[ek]
                 gc_[k_enc] = _graphs.GraphedCompress(net, tuple(x.shape), q, mask_pol, enc_streams[ek],
                                                      slot=0 if ek == 0 else 70 + ek)
             g_enc[i] = gc_[k_enc]
-            wk = i % n_workers
+            wk = p % n_workers
             k_dec = ("dec", dev, zshape, float(q), mask_pol, B, wk)
             if k_dec not in gc_:
                 gc_[k_dec] = _graphs.GraphedDecompress(net, zshape, q, mask_pol, B, net.ns0 if q <= 0 else net.ns1, n_per,
@@ -121,9 +129,10 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
         """Encoder thread ek codes levels ek, ek + n_enc, ... in order and hands each to its decode worker."""
         try:
             with torch.cuda.device(dev), torch.cuda.stream(enc_streams[ek]), torch.no_grad():
-                for i in range(ek, len(qualities), n_enc):
+                for p in range(ek, len(order), n_enc):
                     if err:
                         break
+                    i = order[p]
                     q = qualities[i]
                     xq = x_for_level(q) if x_for_level is not None else x
                     if use_graphs:
@@ -131,7 +140,7 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
                     else:
                         c = net.compress(xq, quality=q, mask_pol=mask_pol, return_device_streams=not host_strings)
                     enc_streams[ek].synchronize()  # compress() has already synchronised to learn the stream lengths
-                    (queues[i % n_workers] if use_graphs else q_items).put((i, q, c))
+                    (queues[p % n_workers] if use_graphs else q_items).put((i, q, c))
         except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
             err.append(e)
 
@@ -150,8 +159,8 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
             q_items.put(None)
         for t in workers:
             t.join()
+    if err:  # (first: after a device fault the stream calls below would raise a less informative error)
+        raise err[0]
     for st in enc_streams + dec_streams:
         caller_stream.wait_stream(st)
-    if err:
-        raise err[0]
     return outs

@@ -480,3 +480,11 @@ def test_graphed_small_batch_sweep_equals_sequential_calls(batch):
             for i, q in enumerate(qs):
                 c = net.compress(x_in, quality=q)
                 assert torch.equal(got[i], net.decompress(c["strings"], c["shape"], quality=q)["x_hat"]), q
+    # Re-preparing the model (any .to() call does, even one that moves nothing: packed weights, tables and arenas are
+    # rebuilt and the old ones freed) must drop the graphs that point into the old state instead of replaying them.
+    old_state = net.prepare()
+    net = net.to("cuda")
+    assert net.prepare() is not old_state
+    got = pipeline.sweep(net, x, qs, graphs=True)
+    for i, q in enumerate(qs):
+        assert torch.equal(got[i], seq[i][1]), ("after re-prepare", q)

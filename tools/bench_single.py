@@ -16,21 +16,21 @@ apply_synthetic_weights(net, seed=0)
 net.update(force=True)
 net = net.cuda()
 x = synthetic_image((1, 3, 512, 768), seed=19).cuda()
-combos = [(g, w) for g in (False, True) for w in (4, 6, 8)]
-if len(sys.argv) > 1:
-    combos = [(bool(int(a.split(",")[0])), int(a.split(",")[1])) for a in sys.argv[1:]]
-for graphs, workers in combos:
+combos = [(g, w, 3) for g in (False, True) for w in (4, 6, 8)]
+if len(sys.argv) > 1:  # graphs,workers,encoders ...
+    combos = [(bool(int(a.split(",")[0])), int(a.split(",")[1]), int(a.split(",")[2])) for a in sys.argv[1:]]
+for graphs, workers, encoders in combos:
     for _ in range(3):
-        pipeline.sweep(net, x, QUALITIES, graphs=graphs, decode_workers=workers, keep=False)
+        pipeline.sweep(net, x, QUALITIES, graphs=graphs, decode_workers=workers, encoders=encoders, keep=False)
     torch.cuda.synchronize()
     ts = []
     for _ in range(5):
         t0 = time.perf_counter()
-        pipeline.sweep(net, x, QUALITIES, graphs=graphs, decode_workers=workers, keep=False)
+        pipeline.sweep(net, x, QUALITIES, graphs=graphs, decode_workers=workers, encoders=encoders, keep=False)
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
     ts.sort()
-    print(f"graphs={graphs} workers {workers}: sweep {1e3 * ts[2]:.0f} ms = {len(QUALITIES) / ts[2]:.1f} image-qualities/s "
+    print(f"graphs={graphs} workers {workers} encoders {encoders}: sweep {1e3 * ts[2]:.0f} ms = {len(QUALITIES) / ts[2]:.1f} image-qualities/s "
           f"(min {1e3 * ts[0]:.0f} ms)", flush=True)
 # single calls at q = 5
 for q in (5,):
