@@ -107,6 +107,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // (same operations, same rounding, same order per element) for ~2/3 of the issue slots.
 struct F2 { unsigned long long v; };
 __device__ __forceinline__ F2 f2_pack(float a, float b) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ F2 f2_pack_bits(unsigned a, unsigned b) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ F2 f2_dup(float a) { return f2_pack(a, a); }
 __device__ __forceinline__ void f2_unpack(F2 p, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
 __device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }

@@ -401,6 +401,15 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       tmem_wait_ld();
       tmem_pin(t0);
       tmem_pin(t1);
+      if (n_hi_used == 1 && n_lo_used == 1) {
+        // the common case of the epilogue-bound layers (short reductions): no accumulator sums, and the combination
+        // runs on packed pairs straight out of the registers the TMEM loads filled (same operations per element)
+        const F2 inv = f2_dup(LO_INV), sc = f2_dup(out_scale);
+#pragma unroll
+        for (int j = 0; j < 16; j += 2)
+          f2_unpack(f2_mul(f2_fma(f2_pack_bits(t1[j], t1[j + 1]), inv, f2_pack_bits(t0[j], t0[j + 1])), sc), acc[j], acc[j + 1]);
+        return;
+      }
       float lo[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) { acc[j] = __uint_as_float(t0[j]); lo[j] = __uint_as_float(t1[j]); }
@@ -477,6 +486,7 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
         const int co = n0 + c0 + 4 * cc;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 bias4 = d.bias ? __ldg(reinterpret_cast<const float4 *>(d.bias + co)) : z4;
+        const F2 bias_xy = f2_pack(bias4.x, bias4.y), bias_zw = f2_pack(bias4.z, bias4.w);
         float acc[16];
         load_acc(c0, acc);
 #pragma unroll
@@ -495,8 +505,10 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
           a1.b = load_res(d.r1, d.r1_pixel_stride, d.r1_16, r1p, opix_t[i + 1], co, ok1);
           a2.a = load_res(d.r2, d.r2_pixel_stride, d.r2_16, r2p, opix_t[i], co, ok0);
           a2.b = load_res(d.r2, d.r2_pixel_stride, d.r2_16, r2p, opix_t[i + 1], co, ok1);
-          v.a = make_float4(v.a.x + bias4.x, v.a.y + bias4.y, v.a.z + bias4.z, v.a.w + bias4.w);
-          v.b = make_float4(v.b.x + bias4.x, v.b.y + bias4.y, v.b.z + bias4.z, v.b.w + bias4.w);
+          f2_unpack(f2_add(f2_pack(v.a.x, v.a.y), bias_xy), v.a.x, v.a.y);
+          f2_unpack(f2_add(f2_pack(v.a.z, v.a.w), bias_zw), v.a.z, v.a.w);
+          f2_unpack(f2_add(f2_pack(v.b.x, v.b.y), bias_xy), v.b.x, v.b.y);
+          f2_unpack(f2_add(f2_pack(v.b.z, v.b.w), bias_zw), v.b.z, v.b.w);
           const F8 o = tc_epilogue8(d.epilogue, v, a1, a2, has_r2);
           if (want_f32) {
             if (ok0) *reinterpret_cast<float4 *>(d.out + opix_t[i] * d.out_pixel_stride + co) = o.a;
