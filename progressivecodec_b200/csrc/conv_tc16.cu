@@ -378,6 +378,20 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
       return make_float4(__fmaf_rn(h_lo_f(l.x), LO_INV, h_lo_f(h.x)), __fmaf_rn(h_hi_f(l.x), LO_INV, h_hi_f(h.x)),
                          __fmaf_rn(h_lo_f(l.y), LO_INV, h_lo_f(h.y)), __fmaf_rn(h_hi_f(l.y), LO_INV, h_hi_f(h.y)));
     };
+    // first residual in two steps (16 raw bytes per row now, the values later) so that its loads can be issued early
+    const bool has_r1 = d.r1 || r1p;
+    auto res_raw = [&](int64_t pix, int co, bool ok) {
+      if (!ok) return make_uint4(0u, 0u, 0u, 0u);
+      if (d.r1) return __ldg(reinterpret_cast<const uint4 *>(d.r1 + pix * d.r1_pixel_stride + co));
+      const uint2 h = __ldg(reinterpret_cast<const uint2 *>(d.r1_16.hi + pix * d.r1_16.pixel_stride + co));
+      const uint2 l = __ldg(reinterpret_cast<const uint2 *>(d.r1_16.lo + pix * d.r1_16.pixel_stride + co));
+      return make_uint4(h.x, h.y, l.x, l.y);
+    };
+    auto res_val = [&](const uint4 &w) {
+      if (d.r1) return make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+      return make_float4(__fmaf_rn(h_lo_f(w.z), LO_INV, h_lo_f(w.x)), __fmaf_rn(h_hi_f(w.z), LO_INV, h_hi_f(w.x)),
+                         __fmaf_rn(h_lo_f(w.w), LO_INV, h_lo_f(w.y)), __fmaf_rn(h_hi_f(w.w), LO_INV, h_hi_f(w.y)));
+    };
     const bool square_planes = (d.flags & PCODEC_FLAG_SQUARE_OUT_PLANES) != 0;
     const float out_scale = __ldg(P.w_scale + 1) * ((d.flags & PCODEC_FLAG_SQUARE_INPUT) ? 256.0f : 1.0f);
 
@@ -493,6 +507,16 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<float4 *>(stg + wr_off + (((uint32_t)q ^ wr_x) << 4)) =
               make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        // Residual rows are fetched ahead of their use (ncu: a fifth of the epilogue warps' stall samples sat on the first
+        // use of these loads): pair (0, 1) before the transposition is complete, pair (2, 3) before pair (0, 1) is
+        // processed.  16 raw bytes per row; the values are formed at the point of use.  (Fetching before the TMEM loads
+        // instead cost registers across them and was slower; an L1 prefetch of the rows was slower too.)
+        uint4 wq[2][2];
+        wq[0][0] = wq[0][1] = wq[1][0] = wq[1][1] = make_uint4(0u, 0u, 0u, 0u);
+        if (has_r1) {
+          wq[0][0] = res_raw(opix_t[0], co, ok_t & 1u);
+          wq[0][1] = res_raw(opix_t[1], co, (ok_t >> 1) & 1u);
+        }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; i += 2) {  // two tile rows (i, i + 1) per call
@@ -501,8 +525,12 @@ conv_taps_tc16_kernel(const __grid_constant__ Params16 P) {
           v.a = *reinterpret_cast<const float4 *>(stg + r0 * 64 + (((uint32_t)cc ^ ((uint32_t)(r0 >> 1) & 3u)) << 4));
           v.b = *reinterpret_cast<const float4 *>(stg + r1_ * 64 + (((uint32_t)cc ^ ((uint32_t)(r1_ >> 1) & 3u)) << 4));
           const bool ok0 = (ok_t >> i) & 1u, ok1 = (ok_t >> (i + 1)) & 1u;
-          a1.a = load_res(d.r1, d.r1_pixel_stride, d.r1_16, r1p, opix_t[i], co, ok0);
-          a1.b = load_res(d.r1, d.r1_pixel_stride, d.r1_16, r1p, opix_t[i + 1], co, ok1);
+          if (i == 0 && has_r1) {  // the second row pair's loads fly while the first pair is processed
+            wq[1][0] = res_raw(opix_t[2], co, (ok_t >> 2) & 1u);
+            wq[1][1] = res_raw(opix_t[3], co, (ok_t >> 3) & 1u);
+          }
+          a1.a = a1.b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_r1) { a1.a = res_val(wq[i >> 1][0]); a1.b = res_val(wq[i >> 1][1]); }
           a2.a = load_res(d.r2, d.r2_pixel_stride, d.r2_16, r2p, opix_t[i], co, ok0);
           a2.b = load_res(d.r2, d.r2_pixel_stride, d.r2_16, r2p, opix_t[i + 1], co, ok1);
           f2_unpack(f2_add(f2_pack(v.a.x, v.a.y), bias_xy), v.a.x, v.a.y);
