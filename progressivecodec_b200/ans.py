@@ -13,6 +13,7 @@ from __future__ import annotations
 
 from typing import List, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -152,20 +153,31 @@ def decode_segments(data: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor
 
 
 def pack_streams(strings: Sequence[bytes], device) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Host byte strings -> (uint8 CUDA blob with 8 bytes of zero slack, int64 CPU offsets)."""
+    """Host byte strings -> (uint8 CUDA blob with 8 bytes of zero slack, int64 CPU offsets).  The blob is staged in pinned
+    host memory and copied on the current stream; the bulk copies are numpy's (they release the GIL, which the pipelined
+    sweep's other host threads are launching kernels under)."""
     lens = [len(s) for s in strings]
     if any(n % 4 for n in lens):  # the device decoder reads aligned 32-bit words (the coder only ever emits whole words)
         raise L.PcodecError("rANS stream length is not a multiple of 4 bytes: not a stream of this coder / corrupted")
     offs = torch.zeros(len(strings) + 1, dtype=torch.int64)
     offs[1:] = torch.cumsum(torch.tensor(lens, dtype=torch.int64), 0)
-    blob = torch.frombuffer(bytearray(b"".join(strings) + b"\0" * 8), dtype=torch.uint8)
-    return blob.to(device, non_blocking=False), offs
+    total = int(offs[-1])
+    host = torch.empty(total + 8, dtype=torch.uint8, pin_memory=True)
+    buf = host.numpy()
+    if total:
+        buf[:total] = np.frombuffer(b"".join(strings), dtype=np.uint8)
+    buf[total:] = 0
+    return host.to(device, non_blocking=True), offs
 
 
 def split_streams(data: torch.Tensor, offsets: torch.Tensor) -> List[bytes]:
-    raw = data.cpu().numpy().tobytes()
+    """uint8 CUDA blob + offsets -> python `bytes` per stream (one device->host copy into pinned memory)."""
+    host = torch.empty(data.numel(), dtype=torch.uint8, pin_memory=True)
+    host.copy_(data, non_blocking=True)
+    torch.cuda.current_stream(data.device).synchronize()
+    raw = host.numpy()
     o = offsets.tolist()
-    return [raw[o[i]:o[i + 1]] for i in range(len(o) - 1)]
+    return [raw[o[i]:o[i + 1]].tobytes() for i in range(len(o) - 1)]
 
 
 def _dev():
