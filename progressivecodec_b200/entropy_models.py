@@ -160,13 +160,11 @@ class EntropyModel(nn.Module):
             raise ValueError("Invalid strings or indexes parameters")
         if len(indexes.size()) < 2:
             raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
-        if means is not None:
+        if means is not None:  # same leading [N, C]; every further dimension either matches or is 1 (broadcast)
             if means.size()[:2] != indexes.size()[:2]:
                 raise ValueError("Invalid means or indexes parameters")
-            if means.size() != indexes.size():
-                for i in range(2, len(indexes.size())):
-                    if means.size(i) != 1:
-                        raise ValueError("Invalid means parameters")
+            if means.size() != indexes.size() and any(means.size(d) != 1 for d in range(2, indexes.dim())):
+                raise ValueError("Invalid means parameters")
         _require_cuda(indexes, "EntropyModel.decompress")
         tables = self.device_tables(indexes.device)
         B = indexes.size(0)
@@ -232,20 +230,21 @@ class EntropyBottleneck(EntropyModel):
         return torch.abs(logits - self.target).sum()
 
     def _logits_cumulative(self, inputs: Tensor, stop_gradient: bool) -> Tensor:
-        """entropy_models.py:400-419 (torch; set-up / training only — the hot path uses the CUDA kernel)."""
-        logits = inputs
-        for i in range(len(self.filters) + 1):
-            matrix = getattr(self, f"_matrix{i:d}")
-            bias = getattr(self, f"_bias{i:d}")
-            if stop_gradient:
-                matrix, bias = matrix.detach(), bias.detach()
-            logits = torch.matmul(F.softplus(matrix), logits) + bias
-            if i < len(self.filters):
-                factor = getattr(self, f"_factor{i:d}")
-                if stop_gradient:
-                    factor = factor.detach()
-                logits = logits + torch.tanh(factor) * torch.tanh(logits)
-        return logits
+        """The per-channel cumulative network of entropy_models.py:400-419: layer k is h <- softplus(M_k) @ h + b_k,
+        followed (all layers but the last) by the gated non-linearity h <- h + tanh(a_k) * tanh(h).  Torch, set-up /
+        training only — the hot path evaluates the same network in pcodec_bottleneck_likelihood."""
+        n_hidden = len(self.filters)
+
+        def param(kind: str, k: int) -> Tensor:
+            p = getattr(self, f"_{kind}{k:d}")
+            return p.detach() if stop_gradient else p
+
+        h = inputs
+        for k in range(n_hidden + 1):
+            h = torch.matmul(F.softplus(param("matrix", k)), h) + param("bias", k)
+            if k != n_hidden:
+                h = h + torch.tanh(param("factor", k)) * torch.tanh(h)
+        return h
 
     def likelihood_params(self, device) -> Tensor:
         """Per-channel packed parameters for pcodec_bottleneck_likelihood: [C, 58] fp32."""
@@ -290,35 +289,30 @@ class EntropyBottleneck(EntropyModel):
 
     @staticmethod
     def _build_indexes(size):
-        """entropy_models.py:491-502."""
-        dims = len(size)
-        N, Cn = size[0], size[1]
-        view_dims = np.ones((dims,), dtype=np.int64)
-        view_dims[1] = -1
-        indexes = torch.arange(Cn).view(*view_dims).int()
-        return indexes.repeat(N, 1, *size[2:])
+        """Channel number of every element of an [N, C, *spatial] tensor, int32 (entropy_models.py:491-502)."""
+        n, ch, spatial = size[0], size[1], tuple(size[2:])
+        per_channel = torch.arange(ch, dtype=torch.int32).reshape(1, ch, *([1] * len(spatial)))
+        return per_channel.repeat(n, 1, *spatial)
 
     @staticmethod
     def _extend_ndims(tensor, n):
         return tensor.reshape(-1, *([1] * n)) if n > 0 else tensor.reshape(-1)
 
+    def _medians_for(self, batch: int, n_spatial: int) -> Tensor:
+        """Per-channel medians broadcast (as a view) to [batch, C, 1 x n_spatial]."""
+        med = self._extend_ndims(self._get_medians().detach(), n_spatial)
+        return med.expand(batch, *([-1] * (n_spatial + 1)))
+
     def compress(self, x):
-        """entropy_models.py:508-515."""
-        indexes = self._build_indexes(x.size()).to(x.device)
-        medians = self._get_medians().detach()
-        spatial_dims = len(x.size()) - 2
-        medians = self._extend_ndims(medians, spatial_dims)
-        medians = medians.expand(x.size(0), *([-1] * (spatial_dims + 1)))
-        return super().compress(x, indexes, medians, 0)
+        """entropy_models.py:508-515: code round(x - median) with one table per channel."""
+        idx = self._build_indexes(x.size()).to(x.device)
+        return super().compress(x, idx, self._medians_for(x.size(0), x.dim() - 2), 0)
 
     def decompress(self, strings, size):
-        """entropy_models.py:517-522."""
-        output_size = (len(strings), self._quantized_cdf.size(0), *size)
-        dev = self.quantiles.device
-        indexes = self._build_indexes(output_size).to(dev)
-        medians = self._extend_ndims(self._get_medians().detach(), len(size))
-        medians = medians.expand(len(strings), *([-1] * (len(size) + 1)))
-        return super().decompress(strings, indexes, medians, 0)
+        """entropy_models.py:517-522: `size` is the spatial shape; one string per batch item."""
+        shape = (len(strings), self._quantized_cdf.size(0), *size)
+        idx = self._build_indexes(shape).to(self.quantiles.device)
+        return super().decompress(strings, idx, self._medians_for(len(strings), len(size)), 0)
 
 
 class GaussianConditional(EntropyModel):
@@ -400,13 +394,12 @@ class GaussianConditional(EntropyModel):
         return sym, idx, lik, yh
 
     def _likelihood(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None) -> Tensor:
-        """entropy_models.py:626-643 in torch (kept for API completeness; forward() uses the fused kernel)."""
-        values = inputs - means if means is not None else inputs
-        scales = self.lower_bound_scale(scales)
-        values = torch.abs(values)
-        upper = self._standardized_cumulative((0.5 - values) / scales)
-        lower = self._standardized_cumulative((-0.5 - values) / scales)
-        return upper - lower
+        """Probability mass of the unit bin around |x - mu| under N(0, max(sigma, bound)) — entropy_models.py:626-643,
+        in torch (kept for API completeness; forward() uses the fused kernel)."""
+        dist = torch.abs(inputs if means is None else inputs - means)
+        sigma = self.lower_bound_scale(scales)
+        cdf = self._standardized_cumulative
+        return cdf((0.5 - dist) / sigma) - cdf((-0.5 - dist) / sigma)
 
     def forward(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None,
                 training: Optional[bool] = None) -> Tuple[Tensor, Tensor]:
