@@ -108,6 +108,76 @@ def test_no_cpu_fallback_and_error_behaviour():
         ChannelProgresssiveWACNN(mask_policy="learnable-mask-gamma")
 
 
+def test_entropy_model_host_contract():
+    """Host-side pieces of the entropy-model API that need no device (reference entropy_models.py:126-165, 261-275,
+    400-419, 491-522, 626-643): quantisation modes, argument validation of decompress(), the bottleneck's channel-index
+    plane and median broadcast, the cumulative network against a per-channel evaluation written out by hand, and the bin
+    likelihood against float64 erfc."""
+    import math
+
+    from progressivecodec_b200 import EntropyBottleneck, GaussianConditional
+    from progressivecodec_b200.entropy_models import EntropyModel
+
+    torch.manual_seed(3)
+    eb = EntropyBottleneck(5)
+    x = torch.randn(2, 5, 3, 4) * 3
+    med = torch.randn(2, 5, 1, 1)
+    assert eb.quantize(x, "symbols", med).dtype == torch.int32
+    assert torch.equal(eb.quantize(x, "symbols", med), torch.round(x - med).int())
+    assert torch.equal(eb.quantize(x, "dequantize", med), torch.round(x - med) + med)
+    assert torch.equal(eb.quantize(x, "dequantize"), torch.round(x))
+    noisy = eb.quantize(x, "noise")
+    assert float((noisy - x).abs().max()) <= 0.5
+    with pytest.raises(ValueError, match="Invalid quantization mode"):
+        eb.quantize(x, "floor")
+    assert torch.equal(eb.dequantize(torch.round(x - med).int(), med), torch.round(x - med) + med)
+
+    idx = eb._build_indexes((2, 5, 3, 4))
+    assert idx.dtype == torch.int32 and idx.shape == (2, 5, 3, 4)
+    assert torch.equal(idx, torch.arange(5).view(1, 5, 1, 1).expand(2, 5, 3, 4).int())
+    assert eb._build_indexes((3, 5)).shape == (3, 5)
+    m = eb._medians_for(2, 2)
+    assert m.shape == (2, 5, 1, 1) and torch.equal(m[1, :, 0, 0], eb.quantiles[:, 0, 1].detach())
+
+    indexes = torch.zeros(2, 5, 3, 4, dtype=torch.int32)
+    with pytest.raises(ValueError, match="Invalid `strings` parameter type"):
+        EntropyModel.decompress(eb, b"xx", indexes)
+    with pytest.raises(ValueError, match="Invalid strings or indexes parameters"):
+        EntropyModel.decompress(eb, [b"x"], indexes)
+    with pytest.raises(ValueError, match="Invalid means or indexes parameters"):
+        EntropyModel.decompress(eb, [b"x", b"y"], indexes, torch.zeros(2, 4, 1, 1))
+    with pytest.raises(ValueError, match="Invalid means parameters"):
+        EntropyModel.decompress(eb, [b"x", b"y"], indexes, torch.zeros(2, 5, 3, 1))
+    with pytest.raises(ValueError, match="same size"):
+        EntropyModel.compress(eb, x, indexes[:, :, :, :3])
+
+    # the cumulative network, one channel at a time, in float64
+    for p in eb.parameters():
+        torch.nn.init.normal_(p, std=0.7)
+    v = torch.linspace(-4, 4, 9).reshape(1, 1, 9).repeat(5, 1, 1)
+    got = eb._logits_cumulative(v, stop_gradient=True)
+    assert not got.requires_grad and eb._logits_cumulative(v, stop_gradient=False).requires_grad
+    for c in range(5):
+        h = v[c].double()
+        for k in range(5):
+            h = torch.nn.functional.softplus(getattr(eb, f"_matrix{k}")[c].detach().double()) @ h + getattr(eb, f"_bias{k}")[c].detach().double()
+            if k < 4:
+                h = h + torch.tanh(getattr(eb, f"_factor{k}")[c].detach().double()) * torch.tanh(h)
+        assert torch.allclose(got[c].double(), h, rtol=1e-5, atol=1e-5)
+
+    gc = GaussianConditional(None)
+    y, mu = torch.randn(64) * 4, torch.randn(64)
+    sc = torch.rand(64) * 3          # some below the 0.11 bound
+    lik = gc._likelihood(y, sc, mu)
+    for i in range(64):
+        d, s = abs(float(y[i]) - float(mu[i])), max(float(sc[i]), float(gc.lower_bound_scale.bound))
+        ref = 0.5 * math.erfc(-(0.5 - d) / s / math.sqrt(2)) - 0.5 * math.erfc(-(-0.5 - d) / s / math.sqrt(2))
+        assert abs(float(lik[i]) - ref) <= 2e-6 + 1e-4 * ref
+    for bad in ([], "abc", [0.5, 0.2], [0.0, 1.0]):
+        with pytest.raises(ValueError):
+            GaussianConditional(bad)
+
+
 def test_synthetic_weights_are_name_keyed_and_deterministic():
     from progressivecodec_b200 import ChannelProgresssiveWACNN, apply_synthetic_weights
 
