@@ -159,6 +159,8 @@ def pack_streams(strings: Sequence[bytes], device) -> Tuple[torch.Tensor, torch.
     lens = [len(s) for s in strings]
     if any(n % 4 for n in lens):  # the device decoder reads aligned 32-bit words (the coder only ever emits whole words)
         raise L.PcodecError("rANS stream length is not a multiple of 4 bytes: not a stream of this coder / corrupted")
+    if any(0 < n < 8 for n in lens):  # every stream ends with the 64-bit coder state (rans_interface.cpp:170-189)
+        raise L.PcodecError("rANS stream shorter than the 8-byte final state: not a stream of this coder / corrupted")
     offs = torch.zeros(len(strings) + 1, dtype=torch.int64)
     offs[1:] = torch.cumsum(torch.tensor(lens, dtype=torch.int64), 0)
     total = int(offs[-1])

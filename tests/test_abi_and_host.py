@@ -102,6 +102,10 @@ def test_no_cpu_fallback_and_error_behaviour():
     gc = GaussianConditional(None)
     with pytest.raises(ValueError, match="Uninitialized CDFs"):
         gc.device_tables("cpu")
+    from progressivecodec_b200 import ans
+    for bad in ([b"abc"], [b"\0" * 8, b"\0" * 6], [b"\0" * 4]):  # validated on the host before anything reaches the device
+        with pytest.raises(PcodecError, match="rANS stream"):
+            ans.pack_streams(bad, "cpu")
     with pytest.raises(NotImplementedError):
         ChannelProgresssiveWACNN(u_net_post=1)
     with pytest.raises(NotImplementedError):
