@@ -233,7 +233,7 @@ def run_ours(args):
                 c = net.compress(x_dev, quality=q, return_device_streams=True)
                 net.decompress(c, c["shape"], quality=q)
         else:  # same calls, compress(q+1) overlapped with decompress(q) on two streams / host threads
-            pipeline.sweep(net, x_dev, QUALITIES, keep=False)
+            pipeline.sweep(net, x_dev, QUALITIES, keep=False, decode_workers=args.decode_workers)
 
     h2d = [0]
     d2h = [0]
@@ -267,7 +267,8 @@ def run_ours(args):
             torch.cuda.current_stream().synchronize()
             _account(q, c, r["x_hat"])
 
-        pipeline.sweep(net, x_dev, QUALITIES, host_strings=True, on_result=on_result, keep=False, x_for_level=_upload)
+        pipeline.sweep(net, x_dev, QUALITIES, host_strings=True, on_result=on_result, keep=False, x_for_level=_upload,
+                       decode_workers=args.decode_workers)
 
     def barrier():
         if world > 1:
@@ -361,11 +362,14 @@ def run_ours(args):
                                                      "larger here than with a trained checkpoint"},
                            "l2": "256 MiB buffer written between steps; working set (0.6 GB weights + activations) >> 126 MB L2",
                            "pipeline": ("none" if args.no_pipeline else
-                                        "compress(q+1) overlaps decompress(q): 2 host threads / CUDA streams (pipeline.sweep)"),
+                                        "compress(q+1) overlaps decompress(q): 2 host threads / CUDA streams (pipeline.sweep)"
+                                        + (f", {args.decode_workers} decode workers" if args.decode_workers else "")),
                            "parallelism": f"dp{world} (images sharded, no collective in the timed region)"},
                 "e2e": {"value": e2e_value, "unit": "image-qualities/s", "h2d_bytes_per_step": h2d[0],
                         "d2h_bytes_per_step": d2h[0], "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+                "hbm_peak_gb": {"allocated": torch.cuda.max_memory_allocated(dev) / 1e9,
+                                "reserved": torch.cuda.max_memory_reserved(dev) / 1e9},
                 "step_algorithmic_tflops": step_tflops, "single_image_latency": lat, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
@@ -466,6 +470,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="compress/decompress strictly back to back")
+    ap.add_argument("--decode-workers", type=int, default=None,
+                    help="concurrent decompress() calls of the pipelined sweep (default: pipeline.sweep's own choice, "
+                         "1 at batch >= 8); tuning experiments only — at the default batch 64 the arenas of a second "
+                         "worker do not fit in 180 GB (clean OutOfMemoryError), use with --batch <= 32")
     ap.add_argument("--dataset", type=int, default=0,
                     help="BASELINE configs[4]: N synthetic 768x512 images SHARDED over the ranks (strong scaling), "
                          "compress+decompress at all 13 levels, per-image stream checksums gathered on rank 0")
