@@ -30,7 +30,8 @@ def sweep(net, x: torch.Tensor, qualities: Sequence[float], mask_pol: Optional[s
     on_result(q, compressed, decompressed) is called on a worker thread after each level (its stream is
     synchronised at that point).  decode_workers: decompress() calls of different levels are independent too, so small
     batches (whose 16-phase decode chain leaves the GPU almost idle) run several of them concurrently; default
-    max(1, min(6, 8 // batch)).  x_for_level(q), when given, is called on the encoder stream before each level and
+    max(1, min(6, 8 // batch)) — every worker owns the activation arenas of its image groups, so at 64 images of 768x512
+    a second worker does not fit in 180 GB (measured: clean OutOfMemoryError at 171 GB).  x_for_level(q), when given, is called on the encoder stream before each level and
     returns that level's input (e.g. a fresh host->device upload); `x` then only fixes the device and batch size.
     With several decode workers the levels are coded in descending quality (the results keep the caller's order): the
     highest levels carry the most symbols, i.e. the longest serial decode chains, and those should start first instead of
