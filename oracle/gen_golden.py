@@ -243,6 +243,58 @@ def run_table800(check: bool):
             print(f"   table800 q={q}: strings identical={same}, x_hat max|d|={err:.3g}")
 
 
+HEADLINE_SHAPE = (1, 3, 512, 768)   # BASELINE.json configs[1]: one 768x512 image
+HEADLINE_QUALITIES = [0, 5]
+HEADLINE_SEED = 0
+
+
+def headline_digest(strings, x_hat: torch.Tensor, x: torch.Tensor) -> dict:
+    """What the headline-shape fixture keeps of one (compress, decompress) result: length and crc32 of every stream, the
+    crc32 of the reconstruction's bytes, its PSNR and a 16x16 average-pooled copy (for hosts whose CPU kernels round
+    differently from the generating one's)."""
+    import zlib
+
+    ys, zs = strings
+    flat = [s for sl in ys for s in sl] + list(zs)
+    mse = float(((x_hat.double() - x.double()) ** 2).mean())
+    return {"lens": np.array([len(s) for s in flat], dtype=np.int64),
+            "crcs": np.array([zlib.crc32(s) for s in flat], dtype=np.uint32),
+            "x_hat_crc": np.uint32(zlib.crc32(x_hat.contiguous().numpy().tobytes())),
+            "psnr": np.float64(10.0 * np.log10(1.0 / mse)),
+            "x_hat_pooled": torch.nn.functional.avg_pool2d(x_hat, 16).numpy()}
+
+
+def run_headline(check: bool):
+    """The shape the bench and BASELINE.json's metric are quoted on (768x512, authors' flags): the REAL reference's
+    compress() / decompress() at q = 0 and 5, kept as digests.  -> tests/golden/headline_768x512.npz"""
+    kwargs, _ = CASES["authors"]
+    net = build_reference(kwargs)
+    x = synthetic_image(HEADLINE_SHAPE, seed=HEADLINE_SEED)
+    rec = {}
+    keep = {}
+    with torch.no_grad():
+        for q in HEADLINE_QUALITIES:
+            c = net.compress(x, quality=q, mask_pol="point-based-std")
+            d = net.decompress(c["strings"], c["shape"], quality=q, mask_pol="point-based-std")
+            keep[q] = (c["strings"], d["x_hat"])
+            for k, v in headline_digest(c["strings"], d["x_hat"], x).items():
+                rec[f"q{q}_{k}"] = v
+    path = os.path.join(GOLD, "headline_768x512.npz")
+    np.savez_compressed(path, **rec)
+    print(f"[golden] headline_768x512: {os.path.getsize(path) / 1024:.0f} KiB")
+    if check:
+        from .codec_port import CodecConfig, OracleCodec
+
+        orc = OracleCodec(net.state_dict(), CodecConfig(**kwargs))
+        for q in HEADLINE_QUALITIES:
+            c = orc.compress(x, quality=q, mask_pol="point-based-std")
+            same = c["strings"][0] == keep[q][0][0] and c["strings"][1] == keep[q][0][1]
+            d = orc.decompress(keep[q][0], c["shape"], quality=q, mask_pol="point-based-std")
+            err = float((d["x_hat"] - keep[q][1]).abs().max())
+            print(f"   headline q={q}: strings identical={same} ({int(rec[f'q{q}_lens'].sum())} bytes), "
+                  f"x_hat max|d|={err:.3g}, psnr {float(rec[f'q{q}_psnr']):.3f} dB")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -254,6 +306,8 @@ def main():
             run_custmap(a.check)
         elif name == "table800":
             run_table800(a.check)
+        elif name == "headline":
+            run_headline(a.check)
         else:
             run_case(name, a.check)
 

@@ -117,6 +117,35 @@ def test_cust_map_masks_match_reference():
             assert abs(psnr(rec, x) - psnr(ref_x, x)) <= 0.02
 
 
+def test_headline_shape_oracle_matches_the_real_reference():
+    """The shape BASELINE.json's metric is quoted on: one 768x512 image, authors' flags, q = 0 and 5.  The fixture
+    (tests/golden/headline_768x512.npz, `python -m oracle.gen_golden --cases headline`) keeps length + crc32 of every
+    stream the REAL reference wrote, the crc32 / PSNR / a pooled copy of its reconstruction; the oracle must reproduce
+    them (bit for bit on the generating CPU; within the north star's bars where another CPU's kernels round differently)."""
+    import zlib
+
+    from oracle.gen_golden import HEADLINE_QUALITIES, HEADLINE_SEED, HEADLINE_SHAPE, headline_digest, synthetic_image
+
+    _net, orc = build_pair("authors")
+    G = load_golden("headline_768x512")
+    x = synthetic_image(HEADLINE_SHAPE, seed=HEADLINE_SEED)
+    for q in HEADLINE_QUALITIES:
+        c = orc.compress(x, quality=q, mask_pol="point-based-std")
+        rec = orc.decompress(c["strings"], tuple(c["shape"]), quality=q, mask_pol="point-based-std")["x_hat"]
+        d = headline_digest(c["strings"], rec, x)
+        n_streams = (10 if q == 0 else 20) + 1
+        assert len(G[f"q{q}_lens"]) == n_streams == len(d["lens"])
+        if np.array_equal(d["crcs"], G[f"q{q}_crcs"]):          # same bytes in => the decoder is deterministic
+            assert np.array_equal(d["lens"], G[f"q{q}_lens"])
+            if int(d["x_hat_crc"]) != int(G[f"q{q}_x_hat_crc"]):
+                assert np.abs(d["x_hat_pooled"] - G[f"q{q}_x_hat_pooled"]).max() <= 1e-4
+        else:
+            ref_bytes = int(G[f"q{q}_lens"].sum())
+            assert abs(int(d["lens"].sum()) - ref_bytes) <= 0.005 * ref_bytes
+        assert abs(float(d["psnr"]) - float(G[f"q{q}_psnr"])) <= 0.02
+        assert zlib.crc32(b"") == 0  # (crc convention of the fixture: plain zlib.crc32 of each stream)
+
+
 def build_table800_pair(device=None):
     """Authors' flags with the reference's 800-level scale table (CHProg_cnn.py:16-26) passed to update()."""
     from conftest import CASE_KWARGS
