@@ -295,6 +295,87 @@ def run_headline(check: bool):
                   f"x_hat max|d|={err:.3g}, psnr {float(rec[f'q{q}_psnr']):.3f} dB")
 
 
+SWEEP_LEVELS = [0, 0.05, 0.1, 0.25, 0.5, 0.6, 0.75, 1, 1.25, 2, 3, 5, 10]   # reference train.py:293
+CONFIG3_SHAPE, CONFIG3_SEED = (16, 3, 256, 256), 11                       # BASELINE.json configs[2]
+CONFIG4_SHAPE, CONFIG4_SEED, CONFIG4_PAD = (1, 3, 1365, 2048), 6, (0, 0, 21, 22)   # configs[3]: CLIC size -> 1408x2048
+CONFIG4_QUALITIES = [0, 5]
+
+
+def config4_image() -> torch.Tensor:
+    return torch.nn.functional.pad(synthetic_image(CONFIG4_SHAPE, seed=CONFIG4_SEED), CONFIG4_PAD)
+
+
+def forward_digest(o: dict, x: torch.Tensor) -> dict:
+    """What the config-3 fixture keeps of forward(x, quality=[levels]): per level the reconstruction's crc32 and PSNR,
+    and the rate the likelihoods imply (bits per pixel, float64 sums); crc32 of the three likelihood tensors."""
+    import zlib
+
+    L = o["x_hat"].shape[0]
+    npx = x.shape[0] * x.shape[2] * x.shape[3]
+    crc = lambda t: np.uint32(zlib.crc32(t.contiguous().numpy().tobytes()))
+    bits = lambda t: float(-torch.log2(t.double()).sum()) / npx
+    yp = o["likelihoods"]["y_prog"]
+    return {"x_hat_crc": np.array([crc(o["x_hat"][l]) for l in range(L)], dtype=np.uint32),
+            "psnr": np.array([10.0 * np.log10(1.0 / float(((o["x_hat"][l].clamp(0, 1).double() - x.double()) ** 2).mean()))
+                              for l in range(L)]),
+            "bpp_y_prog": np.array([bits(yp[l]) for l in range(yp.shape[0])]),
+            "bpp_y": np.float64(bits(o["likelihoods"]["y"])), "bpp_z": np.float64(bits(o["likelihoods"]["z"])),
+            "lik_crc": np.array([crc(o["likelihoods"][k]) for k in ("y", "y_prog", "z")], dtype=np.uint32)}
+
+
+def run_config3(check: bool):
+    """BASELINE.json configs[2]: batched forward() on the 16x3x256x256 training-crop shape at all 13 levels, real
+    reference, kept as digests.  -> tests/golden/config3_forward_16x256x256.npz"""
+    kwargs, _ = CASES["authors"]
+    net = build_reference(kwargs)
+    x = synthetic_image(CONFIG3_SHAPE, seed=CONFIG3_SEED)
+    with torch.no_grad():
+        o = net.forward(x, quality=SWEEP_LEVELS, mask_pol="point-based-std", training=False)
+    rec = forward_digest(o, x)
+    path = os.path.join(GOLD, "config3_forward_16x256x256.npz")
+    np.savez_compressed(path, **rec)
+    print(f"[golden] config3_forward_16x256x256: {os.path.getsize(path) / 1024:.1f} KiB")
+    if check:
+        from .codec_port import CodecConfig, OracleCodec
+
+        orc = OracleCodec(net.state_dict(), CodecConfig(**kwargs))
+        oo = orc.forward(x, quality=SWEEP_LEVELS, mask_pol="point-based-std")
+        d = forward_digest(oo, x)
+        print(f"   config3: x_hat identical at {int((d['x_hat_crc'] == rec['x_hat_crc']).sum())} of {len(SWEEP_LEVELS)} levels, "
+              f"likelihoods identical={bool((d['lik_crc'] == rec['lik_crc']).all())}, "
+              f"x_hat max|d|={float((oo['x_hat'] - o['x_hat']).abs().max()):.3g}")
+
+
+def run_config4(check: bool):
+    """BASELINE.json configs[3] shape: one 2048x1365 image padded to 2048x1408, real reference compress() /
+    decompress() at q = 0 and 5, kept as digests.  -> tests/golden/config4_2048x1408.npz"""
+    kwargs, _ = CASES["authors"]
+    net = build_reference(kwargs)
+    x = config4_image()
+    rec, keep = {}, {}
+    with torch.no_grad():
+        for q in CONFIG4_QUALITIES:
+            c = net.compress(x, quality=q, mask_pol="point-based-std")
+            d = net.decompress(c["strings"], c["shape"], quality=q, mask_pol="point-based-std")
+            keep[q] = (c["strings"], d["x_hat"])
+            for k, v in headline_digest(c["strings"], d["x_hat"], x).items():
+                if k != "x_hat_pooled":
+                    rec[f"q{q}_{k}"] = v
+    path = os.path.join(GOLD, "config4_2048x1408.npz")
+    np.savez_compressed(path, **rec)
+    print(f"[golden] config4_2048x1408: {os.path.getsize(path) / 1024:.1f} KiB")
+    if check:
+        from .codec_port import CodecConfig, OracleCodec
+
+        orc = OracleCodec(net.state_dict(), CodecConfig(**kwargs))
+        for q in CONFIG4_QUALITIES:
+            c = orc.compress(x, quality=q, mask_pol="point-based-std")
+            same = c["strings"][0] == keep[q][0][0] and c["strings"][1] == keep[q][0][1]
+            d = orc.decompress(keep[q][0], c["shape"], quality=q, mask_pol="point-based-std")
+            print(f"   config4 q={q}: strings identical={same} ({int(rec[f'q{q}_lens'].sum())} bytes), "
+                  f"x_hat max|d|={float((d['x_hat'] - keep[q][1]).abs().max()):.3g}, psnr {float(rec[f'q{q}_psnr']):.3f} dB")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
@@ -308,6 +389,10 @@ def main():
             run_table800(a.check)
         elif name == "headline":
             run_headline(a.check)
+        elif name == "config3":
+            run_config3(a.check)
+        elif name == "config4":
+            run_config4(a.check)
         else:
             run_case(name, a.check)
 

@@ -146,6 +146,46 @@ def test_headline_shape_oracle_matches_the_real_reference():
         assert zlib.crc32(b"") == 0  # (crc convention of the fixture: plain zlib.crc32 of each stream)
 
 
+def test_config3_batched_forward_oracle_matches_the_real_reference():
+    """BASELINE.json configs[2]: forward() on 16x3x256x256 at all 13 levels with variance-aware masking.  The fixture
+    (tests/golden/config3_forward_16x256x256.npz, `python -m oracle.gen_golden --cases config3`) holds, per level, the
+    crc32 and PSNR of the REAL reference's reconstruction and the rate its likelihoods imply."""
+    from oracle.gen_golden import CONFIG3_SEED, CONFIG3_SHAPE, SWEEP_LEVELS, forward_digest, synthetic_image
+
+    _net, orc = build_pair("authors")
+    G = load_golden("config3_forward_16x256x256")
+    x = synthetic_image(CONFIG3_SHAPE, seed=CONFIG3_SEED)
+    d = forward_digest(orc.forward(x, quality=SWEEP_LEVELS, mask_pol="point-based-std"), x)
+    assert len(d["psnr"]) == len(SWEEP_LEVELS) == len(G["psnr"]) and len(d["bpp_y_prog"]) == len(G["bpp_y_prog"])
+    if not (np.array_equal(d["x_hat_crc"], G["x_hat_crc"]) and np.array_equal(d["lik_crc"], G["lik_crc"])):
+        assert np.abs(d["psnr"] - G["psnr"]).max() <= 0.02          # another CPU's kernels: the north star's bars
+        assert np.abs(d["bpp_y_prog"] - G["bpp_y_prog"]).max() <= 0.005 * G["bpp_y_prog"].max()
+    assert abs(float(d["bpp_y"]) - float(G["bpp_y"])) <= 0.005 * float(G["bpp_y"])
+    assert abs(float(d["bpp_z"]) - float(G["bpp_z"])) <= 0.005 * float(G["bpp_z"])
+    assert np.all(np.diff(G["bpp_y_prog"]) >= 0)                    # the rate grows with the quality level
+
+
+def test_config4_clic_shape_oracle_matches_the_real_reference():
+    """BASELINE.json configs[3] shape (2048x1365 padded to 2048x1408, slices of 360 448 elements): the oracle against the
+    REAL reference's stream lengths / crc32s and reconstruction at q = 5 (tests/golden/config4_2048x1408.npz)."""
+    from oracle.gen_golden import config4_image, headline_digest
+
+    _net, orc = build_pair("authors")
+    G = load_golden("config4_2048x1408")
+    x = config4_image()
+    q = 5
+    c = orc.compress(x, quality=q, mask_pol="point-based-std")
+    rec = orc.decompress(c["strings"], tuple(c["shape"]), quality=q, mask_pol="point-based-std")["x_hat"]
+    d = headline_digest(c["strings"], rec, x)
+    assert len(d["lens"]) == len(G[f"q{q}_lens"]) == 21
+    ref_bytes = int(G[f"q{q}_lens"].sum())
+    if np.array_equal(d["crcs"], G[f"q{q}_crcs"]):
+        assert np.array_equal(d["lens"], G[f"q{q}_lens"])
+    else:
+        assert abs(int(d["lens"].sum()) - ref_bytes) <= 0.005 * ref_bytes
+    assert abs(float(d["psnr"]) - float(G[f"q{q}_psnr"])) <= 0.02
+
+
 def build_table800_pair(device=None):
     """Authors' flags with the reference's 800-level scale table (CHProg_cnn.py:16-26) passed to update()."""
     from conftest import CASE_KWARGS
