@@ -5,11 +5,11 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from oracle import entropy_port as EP
-from progressivecodec_b200 import ans
+from progressivecodec_b200 import GaussianConditional, ans, get_scale_table
 
-t = EP.GaussianTables.build()
-tables = ans.CdfTables(t.cdf, t.cdf_length, t.offset)
+t = GaussianConditional(None)  # the codec's own 64-level tables (update() through the C-ABI quantiser)
+t.update_scale_table(get_scale_table())
+tables = ans.CdfTables(t._quantized_cdf, t._cdf_length, t._offset)
 g = torch.Generator(device="cuda").manual_seed(0)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 49152
 for S in (1, 2, 8, 32, 168, 672):

@@ -1,10 +1,10 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import entropy_port as EP
-from progressivecodec_b200 import ans
-t = EP.GaussianTables.build()
-tables = ans.CdfTables(t.cdf, t.cdf_length, t.offset)
+from progressivecodec_b200 import GaussianConditional, ans, get_scale_table
+t = GaussianConditional(None)  # the codec's own 64-level tables (update() through the C-ABI quantiser)
+t.update_scale_table(get_scale_table())
+tables = ans.CdfTables(t._quantized_cdf, t._cdf_length, t._offset)
 g = torch.Generator(device="cuda").manual_seed(0)
 S, N = 8, 49152
 sigma = torch.exp(torch.empty((S, N), device="cuda").uniform_(-3.0, 2.0, generator=g))

@@ -1,7 +1,7 @@
 import sys; sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import torch
 from conftest import build_pair
-from oracle.gen_golden import synthetic_image
+from progressivecodec_b200.synthetic import synthetic_image
 from progressivecodec_b200 import container as C
 net, orc = build_pair("allscalable", "cuda")
 x = synthetic_image((2, 3, 128, 192), seed=21)

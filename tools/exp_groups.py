@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import AUTHORS, H, W, QUALITIES
-from oracle.gen_golden import synthetic_image
+from progressivecodec_b200.synthetic import synthetic_image
 from progressivecodec_b200 import ChannelProgresssiveWACNN, apply_synthetic_weights, pipeline
 net = ChannelProgresssiveWACNN(**AUTHORS).eval(); apply_synthetic_weights(net, seed=0); net.update(force=True); net = net.cuda()
 B = int(os.environ.get("B", "32"))

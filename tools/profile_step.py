@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from bench import AUTHORS, H, W
-from oracle.gen_golden import synthetic_image
+from progressivecodec_b200.synthetic import synthetic_image
 from progressivecodec_b200 import ChannelProgresssiveWACNN, _lib, apply_synthetic_weights
 
 ap = argparse.ArgumentParser()
