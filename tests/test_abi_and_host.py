@@ -41,6 +41,45 @@ def test_conv_desc_layout_matches_header():
     assert (ctypes.sizeof(D), D.weight.offset, D.out.offset, D.tc_split.offset) == (size, o_w, o_out, o_r2)
 
 
+def test_library_is_usable_from_plain_c_without_python_or_torch():
+    """The drop-in boundary is a C ABI: a C99 program that includes include/pcodec_b200.h and links
+    libpcodec_b200.so calls a host entry point (pmf_to_quantized_cdf, reference ops.cpp:10-67: known answer
+    {0.5, 0.25, 0.25} -> {0, 32768, 49152, 65536}) with no interpreter in the process, rejects a null argument with a
+    status instead of crashing, and the library's dynamic dependencies name neither python nor torch."""
+    import subprocess
+    import tempfile
+
+    from progressivecodec_b200 import _lib
+
+    src = r"""
+#include <stdio.h>
+#include <stdint.h>
+#include "pcodec_b200.h"
+int main(void) {
+  const float pmf[3] = {0.5f, 0.25f, 0.25f};
+  uint32_t cdf[4] = {1, 1, 1, 1};
+  int rc = pcodec_pmf_to_quantized_cdf(pmf, 3, 16, cdf);
+  int rc_null = pcodec_pmf_to_quantized_cdf(NULL, 3, 16, cdf);
+  printf("%d %u %u %u %u %d %d %s\n", rc, cdf[0], cdf[1], cdf[2], cdf[3], rc_null != 0, pcodec_version() >= 100,
+         pcodec_error_string(rc_null));
+  return 0;
+}
+"""
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "host.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "host")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe,
+                               "-L", libdir, "-lpcodec_b200", "-Wl,-rpath," + libdir])
+        out = subprocess.check_output([exe], text=True).split(None, 7)
+    assert out[:7] == ["0", "0", "32768", "49152", "65536", "1", "1"], out
+    assert out[7].strip(), "pcodec_error_string returned an empty message"
+    needed = [l.split()[-1] for l in subprocess.check_output(["objdump", "-p", _lib.LIB_PATH], text=True).splitlines()
+              if " NEEDED " in l]
+    assert needed and not [n for n in needed if "python" in n or "torch" in n or "c10" in n], needed
+
+
 @pytest.mark.parametrize("case", list(CASE_KWARGS))
 def test_state_dict_keys_match_reference(case):
     from progressivecodec_b200 import ChannelProgresssiveWACNN
